@@ -1,0 +1,396 @@
+"""CPU restatement of the MDGen hot path — TEST INFRASTRUCTURE (the parity oracle).
+
+Plain PyTorch fp32 on the host, functional over a state dict (keys of
+`LatentMDGenModel.state_dict()`), one function per reference routine with its file:line.
+It materialises the attention scores exactly like the reference does, so it is also the
+honest "port" CPU baseline that bench.py times beside the B200 numbers.
+
+Pinned by tests/golden/*.npz, which were produced by running the UNMODIFIED reference
+(/root/reference, imported through oracle/ref_loader.py) on the same seeded inputs; see
+tests/golden/gen_golden.py and tests/test_oracle_golden.py.
+
+Third-party arithmetic the reference delegates to un-vendored packages (fair-esm rotary
+embedding, torchdiffeq fixed-grid Euler) is restated from the packages' published algorithms:
+"parity unpinned by the reference" for those two pieces.
+
+Never imported by mdgen_b200/ (the product).
+"""
+from __future__ import annotations
+
+import math
+import os
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+C = 384
+H = 16
+HD = 24
+IPA_H, IPA_C, IPA_PQ, IPA_PV = 4, 32, 8, 8
+
+_TABLES = None
+
+
+def residue_tables() -> Dict[str, torch.Tensor]:
+    global _TABLES
+    if _TABLES is None:
+        p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                         "mdgen_b200", "data", "residue_tables.npz")
+        z = np.load(p)
+        _TABLES = {k: torch.from_numpy(z[k]) for k in z.files}
+    return _TABLES
+
+
+# --------------------------------------------------------------------------- rigid algebra
+def rot_matmul(a, b):
+    """mdgen/rigid_utils.py:24-61 (written out products, fp32)."""
+    return torch.einsum("...ij,...jk->...ik", a, b)
+
+
+def rot_vec_mul(r, v):
+    """mdgen/rigid_utils.py:64-86."""
+    return torch.einsum("...ij,...j->...i", r, v)
+
+
+def quat_to_rot(q):
+    """mdgen/rigid_utils.py:141-188: standard (w,x,y,z) -> matrix, *no* normalisation."""
+    w, x, y, z = q.unbind(-1)
+    r = torch.stack([
+        w * w + x * x - y * y - z * z, 2 * (x * y - w * z), 2 * (x * z + w * y),
+        2 * (x * y + w * z), w * w - x * x + y * y - z * z, 2 * (y * z - w * x),
+        2 * (x * z - w * y), 2 * (y * z + w * x), w * w - x * x - y * y + z * z,
+    ], -1)
+    return r.reshape(q.shape[:-1] + (3, 3))
+
+
+def rot_to_quat(rot):
+    """mdgen/rigid_utils.py:191-210: top eigenvector of the symmetric 4x4 K matrix / 3
+    (torch.linalg.eigh; eigenvector sign is arbitrary, callers canonicalise w >= 0)."""
+    xx, xy, xz = rot[..., 0, 0], rot[..., 0, 1], rot[..., 0, 2]
+    yx, yy, yz = rot[..., 1, 0], rot[..., 1, 1], rot[..., 1, 2]
+    zx, zy, zz = rot[..., 2, 0], rot[..., 2, 1], rot[..., 2, 2]
+    k = torch.stack([
+        torch.stack([xx + yy + zz, zy - yz, xz - zx, yx - xy], -1),
+        torch.stack([zy - yz, xx - yy - zz, xy + yx, xz + zx], -1),
+        torch.stack([xz - zx, xy + yx, yy - xx - zz, yz + zy], -1),
+        torch.stack([yx - xy, xz + zx, yz + zy, zz - xx - yy], -1),
+    ], -2) * (1.0 / 3.0)
+    _, vec = torch.linalg.eigh(k)
+    return vec[..., -1]
+
+
+def rigid_invert(R, t):
+    """mdgen/rigid_utils.py:1075-1085: (R^T, -R^T t)."""
+    Rt = R.transpose(-1, -2)
+    return Rt, -rot_vec_mul(Rt, t)
+
+
+def rigid_compose(Ra, ta, Rb, tb):
+    """mdgen/rigid_utils.py:1031-1045: (Ra Rb, Ra tb + ta)."""
+    return rot_matmul(Ra, Rb), rot_vec_mul(Ra, tb) + ta
+
+
+def to_tensor_7(R, t, canonical: bool = True):
+    """mdgen/rigid_utils.py:1143-1156 + the w>=0 fix of mdgen/wrapper.py:309."""
+    q = rot_to_quat(R)
+    if canonical:
+        q = q * torch.where(q[..., 0:1] < 0, -1.0, 1.0)
+    return torch.cat([q, t], -1)
+
+
+def get_offsets(R0, t0, R, t):
+    """mdgen/utils.py:7-14: ref.invert().compose(rigids).to_tensor_7(), w>=0
+    (mdgen/wrapper.py:307-309)."""
+    Ri, ti = rigid_invert(R0, t0)
+    Ro, to = rigid_compose(Ri, ti, R, t)
+    return to_tensor_7(Ro, to)
+
+
+# --------------------------------------------------------------------------- small pieces
+def timestep_embedding(t, dim=256, max_period=10000):
+    """mdgen/model/layers.py:30-50."""
+    half = dim // 2
+    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32) / half)
+    args = t[:, None].float() * freqs[None]
+    return torch.cat([torch.cos(args), torch.sin(args)], -1)
+
+
+def t_embedder(sd, t):
+    """mdgen/model/layers.py:52-55 (Linear 256->C, SiLU, Linear C->C)."""
+    h = F.linear(timestep_embedding(t), sd["t_embedder.mlp.0.weight"], sd["t_embedder.mlp.0.bias"])
+    return F.linear(F.silu(h), sd["t_embedder.mlp.2.weight"], sd["t_embedder.mlp.2.bias"])
+
+
+def adaln(sd, prefix, temb):
+    """Sequential(SiLU, Linear) — mdgen/model/latent_model.py:346-349,405-408; layers.py:65-68."""
+    return F.linear(F.silu(temb), sd[prefix + "adaLN_modulation.1.weight"],
+                    sd[prefix + "adaLN_modulation.1.bias"])
+
+
+def layer_norm0(x):
+    """no-affine LayerNorm, eps 1e-6 (mdgen/model/latent_model.py:362,367,439,444)."""
+    return F.layer_norm(x, (x.shape[-1],), None, None, 1e-6)
+
+
+def gelu(x):
+    """erf GELU — mdgen/model/layers.py:77-84."""
+    return x * 0.5 * (1.0 + torch.erf(x / math.sqrt(2.0)))
+
+
+def rope_tables(n: int, inv_freq: torch.Tensor):
+    """fair-esm RotaryEmbedding tables for n positions (see oracle/ref_shims/esm)."""
+    t = torch.arange(n, dtype=torch.float32)
+    freqs = torch.outer(t, inv_freq.float())
+    emb = torch.cat([freqs, freqs], -1)
+    return emb.cos(), emb.sin()
+
+
+def rotate_half(x):
+    x1, x2 = x.chunk(2, -1)
+    return torch.cat([-x2, x1], -1)
+
+
+def mha(sd, prefix, x, mask):
+    """AttentionWithRoPE + MultiheadAttention.forward, batch-first restatement of
+    mdgen/model/latent_model.py:325-329 and mdgen/model/mha.py:260-397.
+    x [Bp,S,C], mask [Bp,S] (1 = real token)."""
+    Bp, S, _ = x.shape
+    p = prefix + "attn."
+    q = F.linear(x, sd[p + "q_proj.weight"], sd[p + "q_proj.bias"]) * (HD ** -0.5)   # :260-263
+    k = F.linear(x, sd[p + "k_proj.weight"], sd[p + "k_proj.bias"])
+    v = F.linear(x, sd[p + "v_proj.weight"], sd[p + "v_proj.bias"])
+    k = torch.cat([k, sd[p + "bias_k"].reshape(1, 1, C).expand(Bp, 1, C)], 1)        # :265-268
+    v = torch.cat([v, sd[p + "bias_v"].reshape(1, 1, C).expand(Bp, 1, C)], 1)
+    pad = torch.cat([1 - mask, mask.new_zeros(Bp, 1)], 1).to(torch.bool)             # :273-280
+    q = q.reshape(Bp, S, H, HD).transpose(1, 2)                                       # :282-286
+    k = k.reshape(Bp, S + 1, H, HD).transpose(1, 2)
+    v = v.reshape(Bp, S + 1, H, HD).transpose(1, 2)
+    cos, sin = rope_tables(S + 1, sd[p + "rot_emb.inv_freq"])                         # :356-357
+    q = q * cos[:S] + rotate_half(q) * sin[:S]
+    k = k * cos + rotate_half(k) * sin
+    w = torch.matmul(q, k.transpose(-1, -2))                                          # :359
+    w = w.masked_fill(pad[:, None, None, :], float("-inf"))                           # :370-376
+    w = F.softmax(w, dim=-1, dtype=torch.float32)                                     # :381
+    o = torch.matmul(w, v).transpose(1, 2).reshape(Bp, S, C)                          # :389-396
+    return F.linear(o, sd[p + "out_proj.weight"], sd[p + "out_proj.bias"])           # :397
+
+
+def ipa(sd, prefix, s, R, t, mask):
+    """InvariantPointAttention.forward with c_z = 0 — mdgen/model/ipa.py:113-255.
+    s [B,L,C]; frames R [B,L,3,3], t [B,L,3]; mask [B,L]."""
+    B, L, _ = s.shape
+    p = prefix + "ipa."
+    q = F.linear(s, sd[p + "linear_q.weight"], sd[p + "linear_q.bias"]).view(B, L, IPA_H, IPA_C)
+    kv = F.linear(s, sd[p + "linear_kv.weight"], sd[p + "linear_kv.bias"]).view(B, L, IPA_H, 2 * IPA_C)
+    k, v = kv[..., :IPA_C], kv[..., IPA_C:]                                           # :123
+    qp = F.linear(s, sd[p + "linear_q_points.weight"], sd[p + "linear_q_points.bias"])
+    qp = torch.stack(torch.split(qp, qp.shape[-1] // 3, -1), -1)                      # :130-131 coord-major
+    qp = rot_vec_mul(R[:, :, None], qp) + t[:, :, None]                               # :132 r.apply
+    qp = qp.view(B, L, IPA_H, IPA_PQ, 3)
+    kvp = F.linear(s, sd[p + "linear_kv_points.weight"], sd[p + "linear_kv_points.bias"])
+    kvp = torch.stack(torch.split(kvp, kvp.shape[-1] // 3, -1), -1)                   # :141-142
+    kvp = rot_vec_mul(R[:, :, None], kvp) + t[:, :, None]
+    kvp = kvp.view(B, L, IPA_H, IPA_PQ + IPA_PV, 3)
+    kp, vp = kvp[..., :IPA_PQ, :], kvp[..., IPA_PQ:, :]                               # :149-151
+    a = torch.einsum("bihc,bjhc->bhij", q, k) * math.sqrt(1.0 / (3 * IPA_C))          # :161-166
+    d2 = ((qp[:, :, None] - kp[:, None]) ** 2).sum(-1)                                # :171-175 [B,i,j,H,P]
+    hw = F.softplus(sd[p + "head_weights"]) * math.sqrt(1.0 / (3 * (IPA_PQ * 9.0 / 2)))  # :176-181
+    pt = (d2 * hw.view(1, 1, 1, IPA_H, 1)).sum(-1) * (-0.5)                           # :182-185
+    sq = 1e5 * (mask[:, :, None] * mask[:, None, :] - 1)                              # :188-190
+    a = a + pt.permute(0, 3, 1, 2) + sq[:, None]                                      # :193-198
+    a = F.softmax(a, -1)                                                              # :203
+    o = torch.einsum("bhij,bjhc->bihc", a, v).reshape(B, L, IPA_H * IPA_C)            # :209-212
+    op = torch.einsum("bhij,bjhpx->bihpx", a, vp)                                     # :216-225
+    op = rot_vec_mul(R.transpose(-1, -2)[:, :, None, None], op - t[:, :, None, None])  # :226 invert_apply
+    opn = torch.sqrt((op ** 2).sum(-1) + 1e-8).reshape(B, L, IPA_H * IPA_PV)          # :229-231
+    op = op.reshape(B, L, IPA_H * IPA_PV, 3)
+    cat = torch.cat([o, op[..., 0], op[..., 1], op[..., 2], opn], -1)                 # :250-251
+    return F.linear(cat, sd[p + "linear_out.weight"], sd[p + "linear_out.bias"])
+
+
+def ipa_layer(sd, prefix, x, temb, mask, R, t):
+    """IPALayer.forward — mdgen/model/latent_model.py:369-384. x [B,L,C], temb [B,C]."""
+    sh_l, sc_l, g_l, sh_m, sc_m, g_m = adaln(sd, prefix, temb).chunk(6, -1)
+    xn = F.layer_norm(x, (C,), sd[prefix + "ipa_norm.weight"], sd[prefix + "ipa_norm.bias"], 1e-5)
+    x = x + ipa(sd, prefix, xn, R, t, mask)                                           # :372
+    res = x
+    h = layer_norm0(x) * (1 + sc_l[:, None]) + sh_l[:, None]                          # :375
+    x = res + g_l[:, None] * mha(sd, prefix + "mha_l.", h, mask)                      # :376-377
+    res = x
+    h = layer_norm0(x) * (1 + sc_m[:, None]) + sh_m[:, None]                          # :380
+    h = F.linear(gelu(F.linear(h, sd[prefix + "fc1.weight"], sd[prefix + "fc1.bias"])),
+                 sd[prefix + "fc2.weight"], sd[prefix + "fc2.bias"])                  # :381
+    return res + g_m[:, None] * h                                                     # :382
+
+
+def mdgen_layer(sd, prefix, x, temb, mask):
+    """LatentMDGenLayer.forward — mdgen/model/latent_model.py:446-483.
+    x [B,T,L,C], temb [B,C], mask [B,T,L]."""
+    B, T, L, _ = x.shape
+    m = adaln(sd, prefix, temb)[:, None, None, :].chunk(9, -1)                        # :449-451
+    sh_l, sc_l, g_l, sh_t, sc_t, g_t, sh_m, sc_m, g_m = m
+    res = x
+    h = layer_norm0(x) * (1 + sc_l) + sh_l                                            # :457
+    h = mha(sd, prefix + "mha_l.", h.reshape(B * T, L, C), mask.reshape(B * T, L)).reshape(B, T, L, C)
+    x = res + g_l * h                                                                 # :462
+    res = x
+    h = layer_norm0(x) * (1 + sc_t) + sh_t                                            # :465
+    h = mha(sd, prefix + "mha_t.", h.transpose(1, 2).reshape(B * L, T, C),
+            mask.transpose(1, 2).reshape(B * L, T)).reshape(B, L, T, C).transpose(1, 2)  # :472-475
+    x = res + g_t * h                                                                 # :476
+    res = x
+    h = layer_norm0(x) * (1 + sc_m) + sh_m                                            # :479
+    h = F.linear(gelu(F.linear(h, sd[prefix + "fc1.weight"], sd[prefix + "fc1.bias"])),
+                 sd[prefix + "fc2.weight"], sd[prefix + "fc2.bias"])                  # :480
+    return res + g_m * h                                                              # :481
+
+
+def run_ipa(sd, cfg, temb, mask_bl, start, end, aatype):
+    """LatentMDGenModel.run_ipa — mdgen/model/latent_model.py:175-210.
+    start/end = (R [B,L,3,3], t [B,L,3]). Deviation (documented in DESIGN.md): the tps branch
+    canonicalises the relative quaternion to w >= 0, the reference leaves eigh's arbitrary sign
+    (mdgen/model/latent_model.py:194-195)."""
+    B, L = mask_bl.shape
+    n = cfg.num_layers
+    if cfg.sim_condition:
+        x = torch.zeros(B, L, C)
+        if aatype is not None and cfg.use_aa_emb:
+            x = x + sd["aatype_to_emb.weight"][aatype]                                # :188
+        for i in range(n):
+            x = ipa_layer(sd, f"ipa_layers.{i}.", x, temb, mask_bl, *start)           # :191-192
+        return x
+    Rs, ts = start
+    Re, te = end
+    x_f = to_tensor_7(*rigid_compose(*rigid_invert(Rs, ts), Re, te))                  # :194
+    x_r = to_tensor_7(*rigid_compose(*rigid_invert(Re, te), Rs, ts))                  # :195
+    x_f = F.linear(x_f, sd["latent_to_emb_f.weight"], sd["latent_to_emb_f.bias"])
+    x_r = F.linear(x_r, sd["latent_to_emb_r.weight"], sd["latent_to_emb_r.bias"])
+    if aatype is not None and cfg.use_aa_emb:
+        x_f = x_f + sd["aatype_to_emb.weight"][aatype]
+        x_r = x_r + sd["aatype_to_emb.weight"][aatype]
+    for i in range(n):
+        x_r = ipa_layer(sd, f"ipa_layers.{i}.", x_r, temb, mask_bl, Rs, ts)           # :205
+        x_f = ipa_layer(sd, f"ipa_layers.{i}.", x_f, temb, mask_bl, Re, te)           # :206
+    return x_r + x_f
+
+
+def forward(sd, cfg, x, t, mask, start, end, x_cond, x_cond_mask, aatype):
+    """LatentMDGenModel.forward (non-design) — mdgen/model/latent_model.py:212-260.
+    x [B,T,L,D], t [B], mask [B,T,L], x_cond [B,T,L,D], x_cond_mask [B,T,L] int64."""
+    h = F.linear(x, sd["latent_to_emb.weight"], sd["latent_to_emb.bias"])             # :233
+    if cfg.abs_pos_emb:
+        h = h + sd["pos_embed"]                                                       # :235
+    if x_cond is not None:
+        h = h + F.linear(x_cond, sd["cond_to_emb.weight"], sd["cond_to_emb.bias"]) \
+            + sd["mask_to_emb.weight"][x_cond_mask]                                   # :241
+    temb = t_embedder(sd, t * cfg.time_multiplier)                                    # :243
+    h = h + run_ipa(sd, cfg, temb, mask[:, 0], start, end, aatype)[:, None]           # :246
+    for i in range(cfg.num_layers):
+        h = mdgen_layer(sd, f"layers.{i}.", h, temb, mask)                            # :248-249
+    sh, sc = adaln(sd, "emb_to_latent.", temb)[:, None, None, :].chunk(2, -1)         # layers.py:71
+    h = layer_norm0(h) * (1 + sc) + sh
+    return F.linear(h, sd["emb_to_latent.linear.weight"], sd["emb_to_latent.linear.bias"])
+
+
+def sample_euler(sd, cfg, zs, t_grid, **kw):
+    """Sampler.sample_ode('euler') -> ode.sample -> torchdiffeq fixed-grid Euler, last state only
+    (mdgen/transport/transport.py:408-451, mdgen/transport/integrators.py:90-113)."""
+    x = zs
+    B = zs.shape[0]
+    for i in range(len(t_grid) - 1):
+        t0, t1 = t_grid[i], t_grid[i + 1]
+        tv = torch.ones(B) * t0                                                       # integrators.py:99
+        x = x + (t1 - t0) * forward(sd, cfg, x, tv, **kw)
+    return x
+
+
+# --------------------------------------------------------------------------- wrapper pieces
+def prep_batch(cfg, batch):
+    """NewMDGenWrapper.prep_batch — mdgen/wrapper.py:283-365 (supported flag subset)."""
+    R, tr = batch["rots"], batch["trans"]
+    B, T, L = tr.shape[:3]
+    off = get_offsets(R[:, 0:1], tr[:, 0:1], R, tr)                                   # :307-309
+    if cfg.tps_condition or cfg.inpainting:
+        off_r = get_offsets(R[:, -1:], tr[:, -1:], R, tr)                             # :315-317
+        off = torch.cat([off, off_r], -1)
+    tors = batch["torsions"].reshape(B, T, L, 14)
+    if getattr(cfg, "no_torsion", False):
+        tors = torch.zeros_like(tors)
+    latents = torch.cat([off, tors], -1)                                              # :327
+    cond_mask = torch.zeros(B, T, L, dtype=torch.int64)
+    if cfg.sim_condition:
+        cond_mask[:, 0] = 1
+    if cfg.tps_condition:
+        cond_mask[:, 0] = 1
+        cond_mask[:, -1] = 1
+    if cfg.cond_interval:
+        cond_mask[:, ::cfg.cond_interval] = 1
+    if cfg.inpainting:
+        cond_mask[:, :, [0, 3]] = 1                                                   # COND_IDX :42,346
+    return {
+        "latents": latents,
+        "start": (R[:, 0], tr[:, 0]),
+        "end": (R[:, -1], tr[:, -1]),
+        "mask": batch["mask"][:, None].expand(-1, T, -1),
+        "aatype": batch["seqres"],
+        "x_cond": torch.where(cond_mask[..., None].bool(), latents, torch.zeros(())),
+        "x_cond_mask": cond_mask,
+    }
+
+
+def torsion_angles_to_frames(R, t, alpha, aatype, tb):
+    """mdgen/geometry.py:273-334. R [...,3,3], t [...,3], alpha [...,7,2], aatype [...]."""
+    d44 = tb["default_frame"][aatype]                                                 # [...,8,4,4]
+    dR, dt = d44[..., :3, :3], d44[..., :3, 3]
+    bb = alpha.new_zeros(alpha.shape[:-2] + (1, 2))
+    bb[..., 1] = 1
+    a = torch.cat([bb, alpha], -2)                                                    # [...,8,2]
+    rot = a.new_zeros(a.shape[:-1] + (3, 3))
+    rot[..., 0, 0] = 1
+    rot[..., 1, 1] = a[..., 1]
+    rot[..., 1, 2] = -a[..., 0]
+    rot[..., 2, 1] = a[..., 0]
+    rot[..., 2, 2] = a[..., 1]
+    fR = rot_matmul(dR, rot)                                                          # default_r.compose(all_rots)
+    ft = dt
+    R5, t5 = fR[..., 5, :, :], ft[..., 5, :]
+    R6, t6 = fR[..., 6, :, :], ft[..., 6, :]
+    R7, t7 = fR[..., 7, :, :], ft[..., 7, :]
+    c1 = (fR[..., 4, :, :], ft[..., 4, :])
+    c2 = rigid_compose(*c1, R5, t5)
+    c3 = rigid_compose(*c2, R6, t6)
+    c4 = rigid_compose(*c3, R7, t7)
+    aR = torch.cat([fR[..., :5, :, :], c2[0][..., None, :, :], c3[0][..., None, :, :],
+                    c4[0][..., None, :, :]], -3)
+    at = torch.cat([ft[..., :5, :], c2[1][..., None, :], c3[1][..., None, :], c4[1][..., None, :]], -2)
+    return rigid_compose(R[..., None, :, :], t[..., None, :], aR, at)                 # r[...,None].compose
+
+
+def frames_to_atom14(gR, gt, aatype, tb):
+    """mdgen/geometry.py:236-270."""
+    gi = tb["atom14_to_group"][aatype].long()                                         # [...,14]
+    oh = F.one_hot(gi, 8).to(gR.dtype)                                                # [...,14,8]
+    aR = torch.einsum("...ag,...gij->...aij", oh, gR)
+    at = torch.einsum("...ag,...gi->...ai", oh, gt)
+    lit = tb["atom14_group_pos"][aatype]
+    pos = rot_vec_mul(aR, lit) + at
+    return pos * tb["atom14_mask"][aatype][..., None]
+
+
+def decode_atom14(cfg, samples, R0, t0, seqres):
+    """Tail of NewMDGenWrapper.inference — mdgen/wrapper.py:456-478 + mdgen/geometry.py:61-79.
+    samples [B,T,L,D]; R0 [B,L,3,3], t0 [B,L,3] = frame-0 rigids; seqres [B,L]."""
+    B, T, L, _ = samples.shape
+    off = samples[..., :7]
+    tors = samples[..., 14:28] if (cfg.tps_condition or cfg.inpainting) else samples[..., 7:21]
+    q = off[..., :4]
+    q = q / torch.sqrt((q ** 2).sum(-1, keepdim=True))                               # rigid_utils.py:324-325
+    fR, ft = rigid_compose(R0[:, None], t0[:, None], quat_to_rot(q), off[..., 4:7])   # :469
+    tors = tors.reshape(B, T, L, 7, 2)
+    tors = tors / torch.linalg.norm(tors, dim=-1, keepdim=True)                       # :476
+    aat = seqres[:, None].expand(B, T, L)
+    tb = residue_tables()
+    gR, gt = torsion_angles_to_frames(fR, ft, tors, aat, tb)
+    return frames_to_atom14(gR, gt, aat, tb)
