@@ -1,0 +1,64 @@
+// Common definitions for the mdgen_b200 device library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+namespace mdgen {
+
+// Fixed architecture (mdgen/parsing.py:87-93 defaults; every published checkpoint uses them).
+constexpr int kC = 384;        // embed_dim
+constexpr int kH = 16;         // mha_heads
+constexpr int kHD = 24;        // head_dim
+constexpr int kHalf = 12;      // rotary half
+constexpr int kFF = 1536;      // ffn dim
+constexpr int kQKV = 3 * kC;   // packed q|k|v projection width
+constexpr int kIpaH = 4, kIpaC = 32, kIpaPq = 8, kIpaPv = 8;
+constexpr int kIpaProj = 128 + 256 + 96 + 192;  // q | kv | q_pts | kv_pts = 672
+constexpr int kIpaCat = kIpaH * (kIpaC + 4 * kIpaPv);  // 256
+constexpr int kTFreq = 256;
+
+// Selects the adaLN modulation row for a token: the table has one row per (step | sample).
+//   sampling: row = *step_ptr (same t for the whole batch, mdgen/transport/integrators.py:98-101)
+//   forward : row = b (per-sample t)
+struct ModRef {
+  const float* base;    // [rows, width]
+  const int* step_ptr;  // device scalar or nullptr
+  int width;            // floats per row
+  int bstride;          // 0 (shared row) or 1 (row per sample)
+  int tokens_per_b;     // tokens per sample in the tensor being processed
+  int bmod;             // batch modulus (two-trunk IPA stacks 2B sequences over B samples)
+};
+
+__device__ __forceinline__ const float* mod_row(const ModRef& m, long long token) {
+  int step = m.step_ptr ? *m.step_ptr : 0;
+  int b = (int)(token / m.tokens_per_b) % m.bmod;
+  return m.base + (size_t)(step + b * m.bstride) * m.width;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Round-to-nearest fp32 -> tf32 (10-bit mantissa), result kept in an fp32 container. Tensor-core
+// kind::tf32 ignores the low 13 mantissa bits, so producers round once here (unbiased) instead
+// of letting the MMA truncate.
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
+__device__ __forceinline__ float gelu_erf(float x) {  // mdgen/model/layers.py:77-84
+  return x * 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
+
+}  // namespace mdgen

@@ -1,0 +1,268 @@
+// Token-wise / small kernels of the MDGen denoiser: timestep embedding, adaLN table,
+// LayerNorm+modulate, token embeddings, final layer + Euler update. All HBM-bound:
+// one warp per token row (384 floats = 3 x float4 per lane), coalesced 128-bit accesses.
+#pragma once
+#include "common.cuh"
+
+namespace mdgen {
+
+// ---------------------------------------------------------------------------------------------
+// Sinusoidal timestep features: emb[r] = [cos(tau f_i) | sin(tau f_i)], tau = t*time_multiplier,
+// f_i = exp(-ln(1e4) i/128)   (mdgen/model/layers.py:30-50, mdgen/model/latent_model.py:243)
+__global__ void sinus_kernel(const float* __restrict__ t, float mult, const float* __restrict__ freqs,
+                             float* __restrict__ emb, int R) {
+  int r = blockIdx.x;
+  int i = threadIdx.x;  // 0..127
+  if (r >= R) return;
+  float a = (t[r] * mult) * freqs[i];
+  emb[(size_t)r * kTFreq + i] = cosf(a);
+  emb[(size_t)r * kTFreq + 128 + i] = sinf(a);
+}
+
+// out[r, j] = act( b[j] + sum_k W[j,k] * in[r,k] ) — one warp per output column j, the weight row
+// lives in registers and is reused for every row r. Used for the t-embedder MLP
+// (mdgen/model/layers.py:23-27) and the concatenated adaLN table (latent_model.py:346-349,405-408;
+// layers.py:65-68). ACT: 0 = none, 1 = SiLU on the output.
+template <int KPL, int ACT>
+__global__ void rowdot_kernel(const float* __restrict__ W, const float* __restrict__ b,
+                              const float* __restrict__ in, float* __restrict__ out, int J, int R) {
+  constexpr int K = KPL * 32;
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (warp >= J) return;
+  float w[KPL];
+#pragma unroll
+  for (int i = 0; i < KPL; ++i) w[i] = W[(size_t)warp * K + i * 32 + lane];
+  float bias = b[warp];
+  for (int r = 0; r < R; ++r) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < KPL; ++i) s = fmaf(w[i], in[(size_t)r * K + i * 32 + lane], s);
+    s = warp_sum(s) + bias;
+    if (ACT == 1) s = silu(s);
+    if (lane == 0) out[(size_t)r * J + warp] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// y = LN0(x) * (1 + scale) + shift  — no-affine LayerNorm eps 1e-6 + adaLN modulate
+// (mdgen/model/layers.py:14-15; latent_model.py:375,380,457,465,479). Optionally rounds the output
+// to TF32 (it only feeds a tensor-core GEMM).
+template <bool ROUND>
+__global__ void ln_mod_kernel(const float* __restrict__ x, float* __restrict__ y, ModRef mod,
+                              int shift_off, int scale_off, long long N) {
+  long long tok = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (tok >= N) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)tok * kC);
+  float4 v[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) v[i] = xr[i * 32 + lane];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  float mean = warp_sum(s) * (1.0f / kC);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / kC) + 1e-6f);
+  const float* mr = mod_row(mod, tok);
+  const float4* sh = reinterpret_cast<const float4*>(mr + shift_off);
+  const float4* sc = reinterpret_cast<const float4*>(mr + scale_off);
+  float4* yr = reinterpret_cast<float4*>(y + (size_t)tok * kC);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    float4 a = sh[i * 32 + lane], b = sc[i * 32 + lane], o;
+    o.x = (v[i].x - mean) * rstd * (1.0f + b.x) + a.x;
+    o.y = (v[i].y - mean) * rstd * (1.0f + b.y) + a.y;
+    o.z = (v[i].z - mean) * rstd * (1.0f + b.z) + a.z;
+    o.w = (v[i].w - mean) * rstd * (1.0f + b.w) + a.w;
+    if (ROUND) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+    yr[i * 32 + lane] = o;
+  }
+}
+
+// Affine LayerNorm eps 1e-5 (IPALayer.ipa_norm, mdgen/model/latent_model.py:351,372).
+template <bool ROUND>
+__global__ void ln_affine_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta,
+                                 long long N) {
+  long long tok = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (tok >= N) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)tok * kC);
+  float4 v[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) v[i] = xr[i * 32 + lane];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  float mean = warp_sum(s) * (1.0f / kC);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / kC) + 1e-5f);
+  const float4* g = reinterpret_cast<const float4*>(gamma);
+  const float4* be = reinterpret_cast<const float4*>(beta);
+  float4* yr = reinterpret_cast<float4*>(y + (size_t)tok * kC);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    float4 a = g[i * 32 + lane], b = be[i * 32 + lane], o;
+    o.x = (v[i].x - mean) * rstd * a.x + b.x;
+    o.y = (v[i].y - mean) * rstd * a.y + b.y;
+    o.z = (v[i].z - mean) * rstd * a.z + b.z;
+    o.w = (v[i].w - mean) * rstd * a.w + b.w;
+    if (ROUND) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+    yr[i * 32 + lane] = o;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Token embeddings (mdgen/model/latent_model.py:233-241). One thread per channel c keeps its
+// weight row (D <= 28 floats) in registers; a block walks a strip of tokens whose D-vectors are
+// staged in shared memory, so global reads/writes are coalesced along c.
+//   MODE 0 (once per sampling call): cond[n,c] = b_lat[c] + pos[l,c] + Wc[c,:]·x_cond[n,:] + b_c[c]
+//                                                + E_mask[x_cond_mask[n]][c]
+//   MODE 1 (every step)            : h[n,c] = Wl[c,:]·x[n,:] + cond[n,c] + ipa[b,l,c]
+constexpr int kEmbedTok = 32;  // tokens per block
+template <int MODE>
+__global__ void __launch_bounds__(kC) embed_kernel(
+    const float* __restrict__ xin, int D, const float* __restrict__ W /*[C,D]*/,
+    const float* __restrict__ bias0, const float* __restrict__ bias1,
+    const float* __restrict__ pos /*[crop,C] or null*/, const float* __restrict__ emask /*[2,C]*/,
+    const int64_t* __restrict__ cmask, const float* __restrict__ cond /*[N,C]*/,
+    const float* __restrict__ ipa /*[B,L,C]*/, float* __restrict__ out, long long N, int T, int L) {
+  __shared__ float xs[kEmbedTok][32];
+  __shared__ int ms[kEmbedTok];
+  int c = threadIdx.x;
+  long long n0 = (long long)blockIdx.x * kEmbedTok;
+  int nt = (int)min((long long)kEmbedTok, N - n0);
+  for (int i = c; i < nt * D; i += kC) xs[i / D][i % D] = xin[(size_t)n0 * D + i];
+  if (MODE == 0 && c < nt) ms[c] = (int)cmask[n0 + c];
+  float w[28];
+#pragma unroll
+  for (int k = 0; k < 28; ++k) w[k] = (k < D) ? W[(size_t)c * D + k] : 0.f;
+  float bsum = (MODE == 0) ? (bias0[c] + bias1[c]) : 0.f;
+  __syncthreads();
+  for (int i = 0; i < nt; ++i) {
+    long long n = n0 + i;
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 28; ++k) s = fmaf(w[k], xs[i][k < D ? k : 0], s);
+    if (MODE == 0) {
+      int l = (int)(n % L);
+      s += bsum;
+      if (pos) s += pos[(size_t)l * kC + c];
+      s += emask[(size_t)ms[i] * kC + c];
+    } else {
+      long long b = n / ((long long)T * L);
+      int l = (int)(n % L);
+      s += cond[(size_t)n * kC + c] + ipa[((size_t)b * L + l) * kC + c];
+    }
+    out[(size_t)n * kC + c] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// FinalLayer (mdgen/model/layers.py:70-74) fused with the Euler update
+// (mdgen/transport/integrators.py:98-113):  v = Linear_{C->D}( LN0(h)*(1+scale)+shift )
+//   EULER = true : x_out[n,:] = x_in[n,:] + dt[*step] * v      (state stays fp32)
+//   EULER = false: x_out[n,:] = v
+// One warp per token; W [D,C] (<= 43 KB) is staged in shared memory once per block.
+template <bool EULER>
+__global__ void __launch_bounds__(256) final_kernel(
+    const float* __restrict__ h, ModRef mod, int shift_off, int scale_off,
+    const float* __restrict__ W /*[D,C]*/, const float* __restrict__ bias, int D,
+    const float* __restrict__ x_in, const float* __restrict__ dt, float* __restrict__ x_out,
+    long long N) {
+  extern __shared__ float ws[];  // [D][C]
+  for (int i = threadIdx.x; i < D * kC; i += blockDim.x) ws[i] = W[i];
+  __syncthreads();
+  int lane = threadIdx.x & 31;
+  int wid = threadIdx.x >> 5;
+  int nw = blockDim.x >> 5;
+  float step_dt = 0.f;
+  if (EULER) step_dt = dt[mod.step_ptr ? *mod.step_ptr : 0];
+  for (long long tok = (long long)blockIdx.x * nw + wid; tok < N; tok += (long long)gridDim.x * nw) {
+    const float4* xr = reinterpret_cast<const float4*>(h + (size_t)tok * kC);
+    float4 v[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) v[i] = xr[i * 32 + lane];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    float mean = warp_sum(s) * (1.0f / kC);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+    float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / kC) + 1e-6f);
+    const float* mr = mod_row(mod, tok);
+    const float4* sh = reinterpret_cast<const float4*>(mr + shift_off);
+    const float4* sc = reinterpret_cast<const float4*>(mr + scale_off);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      float4 a = sh[i * 32 + lane], b = sc[i * 32 + lane];
+      v[i].x = (v[i].x - mean) * rstd * (1.0f + b.x) + a.x;
+      v[i].y = (v[i].y - mean) * rstd * (1.0f + b.y) + a.y;
+      v[i].z = (v[i].z - mean) * rstd * (1.0f + b.z) + a.z;
+      v[i].w = (v[i].w - mean) * rstd * (1.0f + b.w) + a.w;
+    }
+    float mine = 0.f;  // lane d keeps output d
+    for (int d = 0; d < D; ++d) {
+      const float4* wr = reinterpret_cast<const float4*>(ws + d * kC);
+      float p = 0.f;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        float4 w4 = wr[i * 32 + lane];
+        p = fmaf(v[i].x, w4.x, p); p = fmaf(v[i].y, w4.y, p);
+        p = fmaf(v[i].z, w4.z, p); p = fmaf(v[i].w, w4.w, p);
+      }
+      p = warp_sum(p);
+      if (lane == d) mine = p;
+    }
+    if (lane < D) {
+      float vout = mine + bias[lane];
+      size_t o = (size_t)tok * D + lane;
+      x_out[o] = EULER ? fmaf(step_dt, vout, x_in[o]) : vout;
+    }
+  }
+}
+
+__global__ void step_advance_kernel(int* step) { *step += 1; }
+__global__ void step_set_kernel(int* step, int v) { *step = v; }
+
+// dst[r0 + r, c] = round?(scale * src[r, c]) — weight packing (q/k/v concat, head_dim^-0.5 fold).
+__global__ void pack_rows_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                 long long rows, int cols, int dst_ld, long long dst_row0, float scale,
+                                 int do_round) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  long long r = i / cols;
+  int c = (int)(i % cols);
+  float v = src[i] * scale;
+  if (do_round) v = round_tf32(v);
+  dst[(size_t)(dst_row0 + r) * dst_ld + c] = v;
+}
+
+// RoPE tables for positions 0..n-1: cos/sin(pos * inv_freq[i]), i < 12
+// (fair-esm RotaryEmbedding; see oracle/ref_shims/esm/rotary_embedding.py).
+__global__ void rope_table_kernel(const float* __restrict__ inv_freq, float* __restrict__ cosT,
+                                  float* __restrict__ sinT, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * kHalf) return;
+  int pos = i / kHalf, f = i % kHalf;
+  float a = (float)pos * inv_freq[f];
+  cosT[i] = cosf(a);
+  sinT[i] = sinf(a);
+}
+
+}  // namespace mdgen

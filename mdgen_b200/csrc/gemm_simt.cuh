@@ -1,0 +1,114 @@
+// fp32 SIMT GEMM  out = epilogue(A[M,K] · W[N,K]^T + bias).
+// This is the *validation / small-shape* GEMM of the library: exact fp32 FMA arithmetic, any
+// M/N/K/ld. The production path for the large token GEMMs is gemm_tc.cuh (tcgen05 TF32); both
+// share the epilogue definitions below so they can be A/B-checked on the device.
+#pragma once
+#include "common.cuh"
+
+namespace mdgen {
+
+enum EpiMode : int {
+  EPI_STORE = 0,       // out = acc + bias
+  EPI_GELU = 1,        // out = gelu(acc + bias)                   (fc1, layers.py:84)
+  EPI_RESID_GATE = 2,  // out = resid + gate[b] * (acc + bias)     (latent_model.py:462,476,481)
+  EPI_RESID = 3,       // out = resid + (acc + bias)               (x + ipa(...), latent_model.py:372)
+};
+
+struct Epilogue {
+  const float* bias;   // [N] or nullptr
+  const float* resid;  // [M, ldo] (may alias out)
+  ModRef mod;          // gate row source
+  int gate_off;        // column offset of the gate chunk inside the mod row
+  float* out;
+  int ldo;
+  int round_out;       // round result to TF32 (output only feeds another tensor-core GEMM)
+};
+
+template <int MODE>
+__device__ __forceinline__ float apply_epilogue(const Epilogue& ep, float acc, long long m, int n) {
+  float v = acc + (ep.bias ? ep.bias[n] : 0.f);
+  if (MODE == EPI_GELU) v = gelu_erf(v);
+  if (MODE == EPI_RESID_GATE) {
+    const float* mr = mod_row(ep.mod, m);
+    v = ep.resid[(size_t)m * ep.ldo + n] + mr[ep.gate_off + n] * v;
+  }
+  if (MODE == EPI_RESID) v = ep.resid[(size_t)m * ep.ldo + n] + v;
+  if (ep.round_out) v = round_tf32(v);
+  return v;
+}
+
+constexpr int SG_BM = 128, SG_BN = 128, SG_BK = 8;
+
+template <int MODE>
+__global__ void __launch_bounds__(256) gemm_simt_kernel(const float* __restrict__ A, int lda,
+                                                        const float* __restrict__ W, int ldw,
+                                                        long long M, int N, int K, Epilogue ep) {
+  __shared__ __align__(16) float As[2][SG_BK][SG_BM];
+  __shared__ __align__(16) float Bs[2][SG_BK][SG_BN];
+  const int tid = threadIdx.x;
+  const long long m0 = (long long)blockIdx.x * SG_BM;
+  const int n0 = blockIdx.y * SG_BN;
+  // loader mapping: each thread fetches 4 (row, k) elements of A and of W per k-tile
+  const int lrow = tid >> 1;         // 0..127
+  const int lk = (tid & 1) * 4;      // 0 or 4
+  const int ty = tid >> 4, tx = tid & 15;
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  float ra[4], rb[4];
+  auto gload = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int k = k0 + lk + i;
+      long long m = m0 + lrow;
+      int n = n0 + lrow;
+      ra[i] = (m < M && k < K) ? A[(size_t)m * lda + k] : 0.f;
+      rb[i] = (n < N && k < K) ? W[(size_t)n * ldw + k] : 0.f;
+    }
+  };
+  auto sstore = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      As[buf][lk + i][lrow] = ra[i];
+      Bs[buf][lk + i][lrow] = rb[i];
+    }
+  };
+  const int nk = (K + SG_BK - 1) / SG_BK;
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    int buf = kt & 1;
+    if (kt + 1 < nk) gload((kt + 1) * SG_BK);
+#pragma unroll
+    for (int k = 0; k < SG_BK; ++k) {
+      float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
+      float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+      float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tx * 4]);
+      float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (kt + 1 < nk) sstore(buf ^ 1);
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    long long m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+      if (n < N) ep.out[(size_t)m * ep.ldo + n] = apply_epilogue<MODE>(ep, acc[i][j], m, n);
+    }
+  }
+}
+
+}  // namespace mdgen

@@ -1,0 +1,171 @@
+// SE(3) featurisation / decode kernels around the sampler (HBM-bound, one thread per residue).
+//   prep_kernel   == NewMDGenWrapper.prep_batch offsets/latents/cond (mdgen/wrapper.py:283-365)
+//   decode_kernel == inference() tail + frames_torsions_to_atom14
+//                    (mdgen/wrapper.py:456-478, mdgen/geometry.py:61-79,236-334)
+#pragma once
+#include "common.cuh"
+#include "ipa.cuh"
+
+namespace mdgen {
+
+struct PrepFlags {
+  int D;              // 21 | 28
+  int two;            // tps / inpainting: second offset set relative to frame T-1
+  int sim_condition, tps_condition, inpainting, cond_interval, no_torsion;
+};
+
+// Algorithmic bytes per residue: read 36 (rot) + 12 (trans) + 56 (torsions) [+48 ref frames, cached],
+// write 2*4*D (latents, x_cond) + 8 (mask).
+__global__ void prep_kernel(const float* __restrict__ rots, const float* __restrict__ trans,
+                            const float* __restrict__ tors, float* __restrict__ latents,
+                            float* __restrict__ x_cond, int64_t* __restrict__ cmask, int B, int T,
+                            int L, PrepFlags f) {
+  long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long N = (long long)B * T * L;
+  if (n >= N) return;
+  int l = (int)(n % L);
+  int t = (int)((n / L) % T);
+  long long b = n / ((long long)T * L);
+  float R[9], tr[3];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) R[i] = rots[(size_t)n * 9 + i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) tr[i] = trans[(size_t)n * 3 + i];
+  float lat[28];
+  {
+    long long n0 = (b * T + 0) * L + l;
+    float R0[9], t0[3];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R0[i] = rots[(size_t)n0 * 9 + i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) t0[i] = trans[(size_t)n0 * 3 + i];
+    relative_tensor7(R0, t0, R, tr, lat);                      // wrapper.py:307-309
+  }
+  int o = 7;
+  if (f.two) {
+    long long n1 = (b * T + (T - 1)) * L + l;
+    float R1[9], t1[3];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R1[i] = rots[(size_t)n1 * 9 + i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) t1[i] = trans[(size_t)n1 * 3 + i];
+    relative_tensor7(R1, t1, R, tr, lat + 7);                  // wrapper.py:315-317
+    o = 14;
+  }
+#pragma unroll
+  for (int i = 0; i < 14; ++i) lat[o + i] = f.no_torsion ? 0.f : tors[(size_t)n * 14 + i];
+  int cm = 0;                                                   // wrapper.py:338-346
+  if (f.sim_condition && t == 0) cm = 1;
+  if (f.tps_condition && (t == 0 || t == T - 1)) cm = 1;
+  if (f.cond_interval && (t % f.cond_interval) == 0) cm = 1;
+  if (f.inpainting && (l == 0 || l == 3)) cm = 1;
+  cmask[n] = cm;
+  for (int i = 0; i < f.D; ++i) {
+    latents[(size_t)n * f.D + i] = lat[i];
+    x_cond[(size_t)n * f.D + i] = cm ? lat[i] : 0.f;
+  }
+}
+
+struct ResidueTables {
+  const float* default_frame;   // [21,8,4,4]
+  const float* group_pos;       // [21,14,3]
+  const int* atom_group;        // [21,14]
+  const float* atom_mask;       // [21,14]
+};
+
+__device__ __forceinline__ void rmul(const float* A, const float* B, float* Cc) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      Cc[i * 3 + j] = A[i * 3] * B[j] + A[i * 3 + 1] * B[3 + j] + A[i * 3 + 2] * B[6 + j];
+}
+__device__ __forceinline__ void rvec(const float* A, const float* v, float* o) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) o[i] = A[i * 3] * v[0] + A[i * 3 + 1] * v[1] + A[i * 3 + 2] * v[2];
+}
+
+// Algorithmic bytes per residue: read 4*D (sample) [+ frame-0 rigid and tables, cached],
+// write 168 (14 atoms x 3 x fp32).
+__global__ void decode_kernel(const float* __restrict__ samples, int D, int tors_off,
+                              const float* __restrict__ srot, const float* __restrict__ strans,
+                              const int64_t* __restrict__ seqres, ResidueTables tb,
+                              float* __restrict__ atom14, int B, int T, int L) {
+  long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long N = (long long)B * T * L;
+  if (n >= N) return;
+  int l = (int)(n % L);
+  long long b = n / ((long long)T * L);
+  const float* s = samples + (size_t)n * D;
+  // Rigid.from_tensor_7(normalize_quats=True): q / |q| (no eps)   rigid_utils.py:324-325,1158
+  float w = s[0], x = s[1], y = s[2], z = s[3];
+  float qn = 1.0f / sqrtf(w * w + x * x + y * y + z * z);
+  w *= qn; x *= qn; y *= qn; z *= qn;
+  float Rq[9] = {w * w + x * x - y * y - z * z, 2 * (x * y - w * z), 2 * (x * z + w * y),
+                 2 * (x * y + w * z), w * w - x * x + y * y - z * z, 2 * (y * z - w * x),
+                 2 * (x * z - w * y), 2 * (y * z + w * x), w * w - x * x - y * y + z * z};
+  const float* R0 = srot + ((size_t)b * L + l) * 9;
+  const float* t0 = strans + ((size_t)b * L + l) * 3;
+  float Rb[9], tb3[3];
+  rmul(R0, Rq, Rb);                                            // rigids[:,0:1].compose(...)  :469
+  rvec(R0, s + 4, tb3);
+  tb3[0] += t0[0]; tb3[1] += t0[1]; tb3[2] += t0[2];
+  int aa = (int)seqres[(size_t)b * L + l];
+  // 8 rigid groups: default frame ∘ rot_x(torsion)  (geometry.py:273-334); groups 5..7 chained
+  float gR[8][9], gt[8][3];
+  float cR[9], ct[3];   // running chi chain (frame -> backbone)
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    const float* d44 = tb.default_frame + ((size_t)aa * 8 + g) * 16;
+    float dR[9] = {d44[0], d44[1], d44[2], d44[4], d44[5], d44[6], d44[8], d44[9], d44[10]};
+    float dt[3] = {d44[3], d44[7], d44[11]};
+    float a0 = 0.f, a1 = 1.f;                                  // backbone group: (sin, cos) = (0, 1)
+    if (g > 0) {
+      float u = s[tors_off + (g - 1) * 2], v = s[tors_off + (g - 1) * 2 + 1];
+      float nn = 1.0f / sqrtf(u * u + v * v);                  // wrapper.py:476
+      a0 = u * nn; a1 = v * nn;
+    }
+    float rx[9] = {1.f, 0.f, 0.f, 0.f, a1, -a0, 0.f, a0, a1};
+    float fR[9];
+    rmul(dR, rx, fR);
+    if (g <= 4) {
+#pragma unroll
+      for (int i = 0; i < 9; ++i) gR[g][i] = fR[i];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) gt[g][i] = dt[i];
+      if (g == 4) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) cR[i] = fR[i];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) ct[i] = dt[i];
+      }
+    } else {
+      float nR[9], nt[3];
+      rmul(cR, fR, nR);
+      rvec(cR, dt, nt);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) nt[i] += ct[i];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) { gR[g][i] = nR[i]; cR[i] = nR[i]; }
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { gt[g][i] = nt[i]; ct[i] = nt[i]; }
+    }
+  }
+  // to global: backbone ∘ group, then place the 14 atoms (geometry.py:236-270)
+  float* outp = atom14 + (size_t)n * 42;
+#pragma unroll 1
+  for (int a = 0; a < 14; ++a) {
+    int g = tb.atom_group[aa * 14 + a];
+    const float* lp = tb.group_pos + ((size_t)aa * 14 + a) * 3;
+    float p1[3], p2[3];
+    rvec(gR[g], lp, p1);
+    p1[0] += gt[g][0]; p1[1] += gt[g][1]; p1[2] += gt[g][2];
+    rvec(Rb, p1, p2);
+    float mk = tb.atom_mask[aa * 14 + a];
+    outp[a * 3 + 0] = (p2[0] + tb3[0]) * mk;
+    outp[a * 3 + 1] = (p2[1] + tb3[1]) * mk;
+    outp[a * 3 + 2] = (p2[2] + tb3[2]) * mk;
+  }
+}
+
+}  // namespace mdgen

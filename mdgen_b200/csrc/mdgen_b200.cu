@@ -1,0 +1,822 @@
+// libmdgen_b200.so — C-ABI implementation (see include/mdgen_b200.h).
+// Host-side orchestration of the sm_100a kernels: weight packing, workspace, the denoiser step
+// (IPA trunk -> 5 factorised-attention layers -> final layer) and the native Euler loop.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/mdgen_b200.h"
+#include "attention_simt.cuh"
+#include "common.cuh"
+#include "elementwise.cuh"
+#include "gemm_simt.cuh"
+#include "geometry.cuh"
+#include "ipa.cuh"
+#ifndef MDGEN_NO_TC
+#include "gemm_tc.cuh"
+#endif
+
+using namespace mdgen;
+
+namespace {
+
+std::string g_create_error;
+
+struct RawTensor {
+  float* ptr = nullptr;
+  int64_t numel = 0;
+};
+
+// `*_tc` = TF32-rounded (round-to-nearest) copy consumed by the tensor-core GEMMs; the fp32
+// master is kept for the SIMT validation path.
+struct MhaW {
+  float *wqkv, *bqkv, *wo, *bo, *bias_k, *bias_v;
+  float *wqkv_tc, *wo_tc;
+};
+struct IpaLayerW {
+  float *ln_g, *ln_b, *head_w, *wproj, *bproj, *wout, *bout;
+  MhaW mha;
+  float *w1, *b1, *w2, *b2, *w1_tc, *w2_tc;
+};
+struct MainLayerW {
+  MhaW mha_l, mha_t;
+  float *w1, *b1, *w2, *b2, *w1_tc, *w2_tc;
+};
+
+struct ProfEntry {
+  std::string name;
+  cudaEvent_t e0, e1;
+};
+
+}  // namespace
+
+struct mdgen_handle {
+  mdgen_config cfg;
+  std::string err;
+  std::map<std::string, RawTensor> raw;
+  std::vector<void*> allocs;  // everything cudaMalloc'ed by the handle
+  bool finalized = false;
+  int64_t launches = 0;
+#ifdef MDGEN_NO_TC
+  int use_tc = 0;
+#else
+  int use_tc = 1;      // tcgen05 TF32 GEMMs for the token GEMMs (0 = fp32 SIMT validation path)
+#endif
+  int tc_min_rows = 1024;  // below this many rows the SIMT GEMM is used (latency-bound shapes)
+  int profile = 0;
+  std::vector<ProfEntry> prof;
+
+  // packed weights
+  std::vector<IpaLayerW> ipa;
+  std::vector<MainLayerW> layers;
+  float *w_lat = nullptr, *b_lat = nullptr, *w_cond = nullptr, *b_cond = nullptr, *e_mask = nullptr,
+        *pos = nullptr, *aa_emb = nullptr, *wf = nullptr, *bf = nullptr, *wr = nullptr, *br = nullptr;
+  float *w_t0 = nullptr, *b_t0 = nullptr, *w_t2 = nullptr, *b_t2 = nullptr, *w_ada = nullptr,
+        *b_ada = nullptr, *w_fin = nullptr, *b_fin = nullptr, *freqs = nullptr, *inv_freq = nullptr;
+  int modw = 0;
+
+  // RoPE tables
+  float *cosT = nullptr, *sinT = nullptr;
+  int rope_n = 0;
+
+  // residue tables
+  float *tb_frame = nullptr, *tb_pos = nullptr, *tb_mask = nullptr;
+  int* tb_group = nullptr;
+
+  // workspace
+  long long cap_tokens = 0, cap_rows = 0;
+  int cap_modrows = 0;
+  float *h = nullptr, *xn = nullptr, *qkv = nullptr, *att = nullptr, *hid = nullptr, *cond = nullptr;
+  float *xi = nullptr, *xni = nullptr, *proj = nullptr, *cat = nullptr, *qkvi = nullptr, *atti = nullptr,
+        *hidi = nullptr, *frot = nullptr, *ftrans = nullptr, *fmask = nullptr, *ipa_out = nullptr;
+  float *tvals = nullptr, *sinus = nullptr, *h1 = nullptr, *st = nullptr, *mod = nullptr, *dt = nullptr;
+  float *xbuf = nullptr, *xbuf2 = nullptr;  // ping-pong Euler state [N, D<=28]
+  int* step = nullptr;
+};
+
+namespace {
+
+#define CUDA_TRY(h, expr)                                                                   \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      (h)->err = std::string(#expr) + ": " + cudaGetErrorString(_e);                        \
+      return MDGEN_E_CUDA;                                                                  \
+    }                                                                                       \
+  } while (0)
+
+#define CHECK_LAUNCH(h)                                                                     \
+  do {                                                                                      \
+    cudaError_t _e = cudaGetLastError();                                                    \
+    if (_e != cudaSuccess) {                                                                \
+      (h)->err = std::string("kernel launch failed at ") + __FILE__ + ":" +                 \
+                 std::to_string(__LINE__) + ": " + cudaGetErrorString(_e);                  \
+      return MDGEN_E_CUDA;                                                                  \
+    }                                                                                       \
+    (h)->launches++;                                                                        \
+  } while (0)
+
+#define TRY(expr)                 \
+  do {                            \
+    int _rc = (expr);             \
+    if (_rc != MDGEN_OK) return _rc; \
+  } while (0)
+
+struct ProfScope {
+  mdgen_handle* h;
+  cudaStream_t s;
+  int idx = -1;
+  ProfScope(mdgen_handle* h_, cudaStream_t s_, const char* name) : h(h_), s(s_) {
+    if (!h->profile) return;
+    ProfEntry e;
+    e.name = name;
+    cudaEventCreate(&e.e0);
+    cudaEventCreate(&e.e1);
+    cudaEventRecord(e.e0, s);
+    h->prof.push_back(e);
+    idx = (int)h->prof.size() - 1;
+  }
+  ~ProfScope() {
+    if (idx >= 0) cudaEventRecord(h->prof[idx].e1, s);
+  }
+};
+
+int dev_alloc(mdgen_handle* h, void** p, size_t bytes) {
+  if (bytes == 0) bytes = 16;
+  cudaError_t e = cudaMalloc(p, bytes);
+  if (e != cudaSuccess) {
+    h->err = std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e);
+    return MDGEN_E_NOMEM;
+  }
+  h->allocs.push_back(*p);
+  return MDGEN_OK;
+}
+template <typename T>
+int dev_alloc_t(mdgen_handle* h, T** p, size_t n) {
+  return dev_alloc(h, reinterpret_cast<void**>(p), n * sizeof(T));
+}
+void dev_free(mdgen_handle* h, void* p) {
+  if (!p) return;
+  for (size_t i = 0; i < h->allocs.size(); ++i)
+    if (h->allocs[i] == p) {
+      h->allocs.erase(h->allocs.begin() + i);
+      break;
+    }
+  cudaFree(p);
+}
+
+int get_raw(mdgen_handle* h, const std::string& name, int64_t numel, const float** out) {
+  auto it = h->raw.find(name);
+  if (it == h->raw.end()) {
+    h->err = "missing tensor '" + name + "'";
+    return MDGEN_E_WEIGHTS;
+  }
+  if (it->second.numel != numel) {
+    h->err = "tensor '" + name + "' has " + std::to_string(it->second.numel) + " elements, expected " +
+             std::to_string(numel);
+    return MDGEN_E_WEIGHTS;
+  }
+  *out = it->second.ptr;
+  return MDGEN_OK;
+}
+
+// dst[row0 + r, :] = scale * src[r, :]  (optionally TF32-rounded)
+int pack(mdgen_handle* h, cudaStream_t s, const std::string& name, long long rows, int cols, float* dst,
+         int dst_ld, long long row0, float scale, int do_round) {
+  const float* src;
+  TRY(get_raw(h, name, rows * cols, &src));
+  long long n = rows * cols;
+  pack_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src, dst, rows, cols, dst_ld, row0, scale,
+                                                                do_round);
+  CHECK_LAUNCH(h);
+  return MDGEN_OK;
+}
+
+int pack_new(mdgen_handle* h, cudaStream_t s, const std::string& name, long long rows, int cols, float** dst,
+             float scale = 1.f, int do_round = 0) {
+  TRY(dev_alloc_t(h, dst, (size_t)rows * cols));
+  return pack(h, s, name, rows, cols, *dst, cols, 0, scale, do_round);
+}
+
+// TF32-rounded copy of an already packed fp32 matrix.
+int tc_copy(mdgen_handle* h, cudaStream_t s, const float* src, size_t n, float** dst) {
+  TRY(dev_alloc_t(h, dst, n));
+  pack_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src, *dst, 1, (int)n, (int)n, 0, 1.f, 1);
+  CHECK_LAUNCH(h);
+  return MDGEN_OK;
+}
+
+int pack_mha(mdgen_handle* h, cudaStream_t s, const std::string& p, MhaW* w) {
+  const float scale = 0.20412414523193154f;  // 24^-0.5 folded into W_q, b_q (mha.py:102,263)
+  TRY(dev_alloc_t(h, &w->wqkv, (size_t)kQKV * kC));
+  TRY(dev_alloc_t(h, &w->bqkv, (size_t)kQKV));
+  TRY(pack(h, s, p + "attn.q_proj.weight", kC, kC, w->wqkv, kC, 0, scale, 0));
+  TRY(pack(h, s, p + "attn.k_proj.weight", kC, kC, w->wqkv, kC, kC, 1.f, 0));
+  TRY(pack(h, s, p + "attn.v_proj.weight", kC, kC, w->wqkv, kC, 2 * kC, 1.f, 0));
+  TRY(tc_copy(h, s, w->wqkv, (size_t)kQKV * kC, &w->wqkv_tc));
+  TRY(pack(h, s, p + "attn.q_proj.bias", 1, kC, w->bqkv, kQKV, 0, scale, 0));
+  TRY(pack(h, s, p + "attn.k_proj.bias", 1, kC, w->bqkv + kC, kQKV, 0, 1.f, 0));
+  TRY(pack(h, s, p + "attn.v_proj.bias", 1, kC, w->bqkv + 2 * kC, kQKV, 0, 1.f, 0));
+  TRY(pack_new(h, s, p + "attn.out_proj.weight", kC, kC, &w->wo));
+  TRY(tc_copy(h, s, w->wo, (size_t)kC * kC, &w->wo_tc));
+  TRY(pack_new(h, s, p + "attn.out_proj.bias", 1, kC, &w->bo));
+  TRY(pack_new(h, s, p + "attn.bias_k", 1, kC, &w->bias_k));
+  TRY(pack_new(h, s, p + "attn.bias_v", 1, kC, &w->bias_v));
+  return MDGEN_OK;
+}
+
+int ensure_rope(mdgen_handle* h, cudaStream_t s, int n) {
+  if (n <= h->rope_n) return MDGEN_OK;
+  int cap = n + 64;
+  if (h->cosT) { dev_free(h, h->cosT); dev_free(h, h->sinT); }
+  TRY(dev_alloc_t(h, &h->cosT, (size_t)cap * kHalf));
+  TRY(dev_alloc_t(h, &h->sinT, (size_t)cap * kHalf));
+  rope_table_kernel<<<(cap * kHalf + 255) / 256, 256, 0, s>>>(h->inv_freq, h->cosT, h->sinT, cap);
+  CHECK_LAUNCH(h);
+  h->rope_n = cap;
+  return MDGEN_OK;
+}
+
+int ensure_workspace(mdgen_handle* h, long long N, long long rows, int modrows) {
+  if (N > h->cap_tokens) {
+    float** bufs[] = {&h->h, &h->xn, &h->qkv, &h->att, &h->hid, &h->cond, &h->xbuf, &h->xbuf2};
+    for (auto b : bufs) { dev_free(h, *b); *b = nullptr; }
+    // +128 rows of slack so tensor-core tiles may over-read the last partial tile
+    size_t n = (size_t)N + 128;
+    TRY(dev_alloc_t(h, &h->h, n * kC));
+    TRY(dev_alloc_t(h, &h->xn, n * kC));
+    TRY(dev_alloc_t(h, &h->qkv, n * kQKV));
+    TRY(dev_alloc_t(h, &h->att, n * kC));
+    TRY(dev_alloc_t(h, &h->hid, n * kFF));
+    TRY(dev_alloc_t(h, &h->cond, n * kC));
+    TRY(dev_alloc_t(h, &h->xbuf, n * 28));
+    TRY(dev_alloc_t(h, &h->xbuf2, n * 28));
+    h->cap_tokens = N;
+  }
+  if (rows > h->cap_rows) {
+    float** bufs[] = {&h->xi, &h->xni, &h->proj, &h->cat, &h->qkvi, &h->atti, &h->hidi,
+                      &h->frot, &h->ftrans, &h->fmask, &h->ipa_out};
+    for (auto b : bufs) { dev_free(h, *b); *b = nullptr; }
+    size_t n = (size_t)rows + 128;
+    TRY(dev_alloc_t(h, &h->xi, n * kC));
+    TRY(dev_alloc_t(h, &h->xni, n * kC));
+    TRY(dev_alloc_t(h, &h->proj, n * kIpaProj));
+    TRY(dev_alloc_t(h, &h->cat, n * kIpaCat));
+    TRY(dev_alloc_t(h, &h->qkvi, n * kQKV));
+    TRY(dev_alloc_t(h, &h->atti, n * kC));
+    TRY(dev_alloc_t(h, &h->hidi, n * kFF));
+    TRY(dev_alloc_t(h, &h->frot, n * 9));
+    TRY(dev_alloc_t(h, &h->ftrans, n * 3));
+    TRY(dev_alloc_t(h, &h->fmask, n));
+    TRY(dev_alloc_t(h, &h->ipa_out, n * kC));
+    h->cap_rows = rows;
+  }
+  if (modrows > h->cap_modrows) {
+    float** bufs[] = {&h->tvals, &h->sinus, &h->h1, &h->st, &h->mod, &h->dt};
+    for (auto b : bufs) { dev_free(h, *b); *b = nullptr; }
+    size_t r = (size_t)modrows;
+    TRY(dev_alloc_t(h, &h->tvals, r));
+    TRY(dev_alloc_t(h, &h->sinus, r * kTFreq));
+    TRY(dev_alloc_t(h, &h->h1, r * kC));
+    TRY(dev_alloc_t(h, &h->st, r * kC));
+    TRY(dev_alloc_t(h, &h->mod, r * h->modw));
+    TRY(dev_alloc_t(h, &h->dt, r));
+    h->cap_modrows = modrows;
+  }
+  if (!h->step) TRY(dev_alloc_t(h, &h->step, 4));
+  return MDGEN_OK;
+}
+
+// ---- GEMM dispatch ---------------------------------------------------------------------------
+int gemm(mdgen_handle* h, cudaStream_t s, int mode, const float* A, int lda, const float* W,
+         const float* W_tc, int ldw, long long M, int N, int K, const Epilogue& ep, const char* tag) {
+  ProfScope ps(h, s, tag);
+#ifndef MDGEN_NO_TC
+  if (h->use_tc && W_tc && M >= h->tc_min_rows && tc_gemm_supported(N, K)) {
+    int rc = tc_gemm_launch(mode, A, lda, W_tc, ldw, M, N, K, ep, s, &h->err);
+    if (rc != MDGEN_OK) return rc;
+    h->launches++;
+    return MDGEN_OK;
+  }
+#endif
+  dim3 grid((unsigned)((M + SG_BM - 1) / SG_BM), (unsigned)((N + SG_BN - 1) / SG_BN));
+  switch (mode) {
+    case EPI_STORE: gemm_simt_kernel<EPI_STORE><<<grid, 256, 0, s>>>(A, lda, W, ldw, M, N, K, ep); break;
+    case EPI_GELU: gemm_simt_kernel<EPI_GELU><<<grid, 256, 0, s>>>(A, lda, W, ldw, M, N, K, ep); break;
+    case EPI_RESID_GATE: gemm_simt_kernel<EPI_RESID_GATE><<<grid, 256, 0, s>>>(A, lda, W, ldw, M, N, K, ep); break;
+    case EPI_RESID: gemm_simt_kernel<EPI_RESID><<<grid, 256, 0, s>>>(A, lda, W, ldw, M, N, K, ep); break;
+    default: h->err = "bad epilogue mode"; return MDGEN_E_INVALID;
+  }
+  CHECK_LAUNCH(h);
+  return MDGEN_OK;
+}
+
+Epilogue make_epi(const float* bias, float* out, int ldo, int round_out = 0) {
+  Epilogue e;
+  memset(&e, 0, sizeof(e));
+  e.bias = bias; e.out = out; e.ldo = ldo; e.round_out = round_out;
+  return e;
+}
+Epilogue make_epi_gate(const float* bias, float* x, int ldo, const ModRef& mod, int gate_off) {
+  Epilogue e = make_epi(bias, x, ldo);
+  e.resid = x; e.mod = mod; e.gate_off = gate_off;
+  return e;
+}
+
+int attention(mdgen_handle* h, cudaStream_t s, const float* qkv, const float* mask, const MhaW& w,
+              float* out, const SeqMap& sm, int round_out, const char* tag) {
+  ProfScope ps(h, s, tag);
+  AttnParams p;
+  p.qkv = qkv; p.mask = mask; p.bias_k = w.bias_k; p.bias_v = w.bias_v;
+  p.cosT = h->cosT; p.sinT = h->sinT; p.out = out; p.round_out = round_out; p.sm = sm;
+  if (sm.S <= 64) {
+    long long total = sm.num_seq * sm.S * kH;
+    attn_small_kernel<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(p);
+  } else {
+    dim3 grid((sm.S + AF_QT - 1) / AF_QT, kH, (unsigned)sm.num_seq);
+    attn_flash_simt_kernel<<<grid, 128, 0, s>>>(p);
+  }
+  CHECK_LAUNCH(h);
+  return MDGEN_OK;
+}
+
+template <bool ROUND>
+int ln_mod(mdgen_handle* h, cudaStream_t s, const float* x, float* y, const ModRef& mod, int shift_off,
+           int scale_off, long long N) {
+  ProfScope ps(h, s, "ln_mod");
+  unsigned blocks = (unsigned)((N * 32 + 255) / 256);
+  ln_mod_kernel<ROUND><<<blocks, 256, 0, s>>>(x, y, mod, shift_off, scale_off, N);
+  CHECK_LAUNCH(h);
+  return MDGEN_OK;
+}
+
+int check_cond(mdgen_handle* h, const mdgen_cond* c) {
+  if (!h->finalized) { h->err = "weights not finalised"; return MDGEN_E_WEIGHTS; }
+  if (!c || c->B <= 0 || c->T <= 0 || c->L <= 0) { h->err = "bad cond dims"; return MDGEN_E_INVALID; }
+  if (!c->mask || !c->start_rot || !c->start_trans || !c->x_cond || !c->x_cond_mask) {
+    h->err = "cond: mask/start frames/x_cond/x_cond_mask are required"; return MDGEN_E_INVALID;
+  }
+  bool two = !h->cfg.sim_condition && (h->cfg.tps_condition || h->cfg.inpainting);
+  if (two && (!c->end_rot || !c->end_trans)) { h->err = "cond: end frames required"; return MDGEN_E_INVALID; }
+  if (h->cfg.use_aa_emb && !c->aatype) { h->err = "cond: aatype required"; return MDGEN_E_INVALID; }
+  if (h->cfg.abs_pos_emb && c->L != h->cfg.crop) {
+    h->err = "abs_pos_emb requires L == crop"; return MDGEN_E_INVALID;
+  }
+  return MDGEN_OK;
+}
+
+// Timestep embedding + every adaLN modulation vector for `R` time rows (tvals already on device).
+int build_mod_table(mdgen_handle* h, cudaStream_t s, int R) {
+  ProfScope ps(h, s, "adaln_table");
+  sinus_kernel<<<R, 128, 0, s>>>(h->tvals, h->cfg.time_multiplier, h->freqs, h->sinus, R);
+  CHECK_LAUNCH(h);
+  rowdot_kernel<8, 1><<<(kC * 32 + 255) / 256, 256, 0, s>>>(h->w_t0, h->b_t0, h->sinus, h->h1, kC, R);
+  CHECK_LAUNCH(h);
+  // st = SiLU(temb): every consumer applies SiLU first (Sequential(SiLU, Linear))
+  rowdot_kernel<12, 1><<<(kC * 32 + 255) / 256, 256, 0, s>>>(h->w_t2, h->b_t2, h->h1, h->st, kC, R);
+  CHECK_LAUNCH(h);
+  rowdot_kernel<12, 0><<<(unsigned)(((long long)h->modw * 32 + 255) / 256), 256, 0, s>>>(
+      h->w_ada, h->b_ada, h->st, h->mod, h->modw, R);
+  CHECK_LAUNCH(h);
+  return MDGEN_OK;
+}
+
+// Step-invariant conditioning embedding (latent_model.py:233-241 minus latent_to_emb(x)).
+int build_cond(mdgen_handle* h, cudaStream_t s, const mdgen_cond* c) {
+  ProfScope ps(h, s, "cond_embed");
+  long long N = (long long)c->B * c->T * c->L;
+  embed_kernel<0><<<(unsigned)((N + kEmbedTok - 1) / kEmbedTok), kC, 0, s>>>(
+      c->x_cond, h->cfg.latent_dim, h->w_cond, h->b_lat, h->b_cond, h->pos, h->e_mask, c->x_cond_mask,
+      nullptr, nullptr, h->cond, N, c->T, c->L);
+  CHECK_LAUNCH(h);
+  return MDGEN_OK;
+}
+
+// One denoiser evaluation on state x_in. euler: x_out = x_in + dt[step] * v ; else x_out = v.
+int run_step(mdgen_handle* h, cudaStream_t s, const mdgen_cond* c, const float* x_in, float* x_out,
+             bool euler, const int* step_ptr, int bstride) {
+  const int B = c->B, T = c->T, L = c->L, n = h->cfg.num_layers, D = h->cfg.latent_dim;
+  const long long N = (long long)B * T * L;
+  const bool two = !h->cfg.sim_condition && (h->cfg.tps_condition || h->cfg.inpainting);
+  const long long BL = (long long)B * L, rows = (two ? 2 : 1) * BL;
+  const int rt = h->use_tc ? 1 : 0;  // round GEMM-operand activations to TF32
+
+  ModRef modi{h->mod, step_ptr, h->modw, bstride, L, B};
+  ModRef modm{h->mod, step_ptr, h->modw, bstride, T * L, B};
+
+  // ---------------- IPA trunk on the key frame(s)  (latent_model.py:175-210, 369-384)
+  {
+    ProfScope ps(h, s, "ipa_trunk");
+    ipa_init_kernel<<<(unsigned)rows, kC, 0, s>>>(two ? 1 : 0, c->start_rot, c->start_trans, c->end_rot,
+                                                 c->end_trans, c->aatype,
+                                                 h->cfg.use_aa_emb ? h->aa_emb : nullptr, h->wf, h->bf,
+                                                 h->wr, h->br, c->mask, T, L, h->xi, h->frot, h->ftrans,
+                                                 h->fmask, BL);
+    CHECK_LAUNCH(h);
+    SeqMap smi{L, rows, 1, (long long)L, 0, 1};
+    for (int i = 0; i < n; ++i) {
+      const IpaLayerW& w = h->ipa[i];
+      int off = i * 6 * kC;
+      ln_affine_kernel<false><<<(unsigned)((rows * 32 + 255) / 256), 256, 0, s>>>(h->xi, h->xni, w.ln_g,
+                                                                                w.ln_b, rows);
+      CHECK_LAUNCH(h);
+      TRY(gemm(h, s, EPI_STORE, h->xni, kC, w.wproj, nullptr, kC, rows, kIpaProj, kC,
+               make_epi(w.bproj, h->proj, kIpaProj), "ipa_gemm"));
+      ipa_points_kernel<<<(unsigned)((rows * 96 + 255) / 256), 256, 0, s>>>(h->proj, h->frot, h->ftrans, rows);
+      CHECK_LAUNCH(h);
+      ipa_attn_kernel<<<(unsigned)rows, 128, 4 * L * sizeof(float), s>>>(h->proj, h->frot, h->ftrans, h->fmask,
+                                                                         w.head_w, h->cat, L, 0);
+      CHECK_LAUNCH(h);
+      Epilogue eo = make_epi(w.bout, h->xi, kC);
+      eo.resid = h->xi;
+      TRY(gemm(h, s, EPI_RESID, h->cat, kIpaCat, w.wout, nullptr, kIpaCat, rows, kC, kIpaCat, eo, "ipa_gemm"));
+      TRY(ln_mod<false>(h, s, h->xi, h->xni, modi, off + 0, off + kC, rows));
+      TRY(gemm(h, s, EPI_STORE, h->xni, kC, w.mha.wqkv, nullptr, kC, rows, kQKV, kC,
+               make_epi(w.mha.bqkv, h->qkvi, kQKV), "ipa_gemm"));
+      TRY(attention(h, s, h->qkvi, h->fmask, w.mha, h->atti, smi, 0, "ipa_mha"));
+      TRY(gemm(h, s, EPI_RESID_GATE, h->atti, kC, w.mha.wo, nullptr, kC, rows, kC, kC,
+               make_epi_gate(w.mha.bo, h->xi, kC, modi, off + 2 * kC), "ipa_gemm"));
+      TRY(ln_mod<false>(h, s, h->xi, h->xni, modi, off + 3 * kC, off + 4 * kC, rows));
+      TRY(gemm(h, s, EPI_GELU, h->xni, kC, w.w1, nullptr, kC, rows, kFF, kC, make_epi(w.b1, h->hidi, kFF), "ipa_gemm"));
+      TRY(gemm(h, s, EPI_RESID_GATE, h->hidi, kFF, w.w2, nullptr, kFF, rows, kC, kFF,
+               make_epi_gate(w.b2, h->xi, kC, modi, off + 5 * kC), "ipa_gemm"));
+    }
+    long long ne = BL * kC;
+    ipa_sum_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, s>>>(h->xi, h->ipa_out, ne, two ? 1 : 0);
+    CHECK_LAUNCH(h);
+  }
+
+  // ---------------- token embedding  (latent_model.py:233-246)
+  {
+    ProfScope ps(h, s, "embed");
+    embed_kernel<1><<<(unsigned)((N + kEmbedTok - 1) / kEmbedTok), kC, 0, s>>>(
+        x_in, D, h->w_lat, nullptr, nullptr, nullptr, nullptr, nullptr, h->cond, h->ipa_out, h->h, N, T, L);
+    CHECK_LAUNCH(h);
+  }
+
+  // ---------------- main layers  (latent_model.py:446-483)
+  SeqMap sml{L, (long long)B * T, 1, (long long)L, 0, 1};
+  SeqMap smt{T, (long long)B * L, L, (long long)T * L, 1, L};
+  for (int i = 0; i < n; ++i) {
+    const MainLayerW& w = h->layers[i];
+    int off = n * 6 * kC + i * 9 * kC;
+    // residue attention (over L)
+    if (rt) TRY(ln_mod<true>(h, s, h->h, h->xn, modm, off + 0, off + kC, N));
+    else TRY(ln_mod<false>(h, s, h->h, h->xn, modm, off + 0, off + kC, N));
+    TRY(gemm(h, s, EPI_STORE, h->xn, kC, w.mha_l.wqkv, w.mha_l.wqkv_tc, kC, N, kQKV, kC,
+             make_epi(w.mha_l.bqkv, h->qkv, kQKV), "gemm_qkv"));
+    TRY(attention(h, s, h->qkv, c->mask, w.mha_l, h->att, sml, rt, "mha_l"));
+    TRY(gemm(h, s, EPI_RESID_GATE, h->att, kC, w.mha_l.wo, w.mha_l.wo_tc, kC, N, kC, kC,
+             make_epi_gate(w.mha_l.bo, h->h, kC, modm, off + 2 * kC), "gemm_out"));
+    // time attention (over T)
+    if (rt) TRY(ln_mod<true>(h, s, h->h, h->xn, modm, off + 3 * kC, off + 4 * kC, N));
+    else TRY(ln_mod<false>(h, s, h->h, h->xn, modm, off + 3 * kC, off + 4 * kC, N));
+    TRY(gemm(h, s, EPI_STORE, h->xn, kC, w.mha_t.wqkv, w.mha_t.wqkv_tc, kC, N, kQKV, kC,
+             make_epi(w.mha_t.bqkv, h->qkv, kQKV), "gemm_qkv"));
+    TRY(attention(h, s, h->qkv, c->mask, w.mha_t, h->att, smt, rt, "mha_t"));
+    TRY(gemm(h, s, EPI_RESID_GATE, h->att, kC, w.mha_t.wo, w.mha_t.wo_tc, kC, N, kC, kC,
+             make_epi_gate(w.mha_t.bo, h->h, kC, modm, off + 5 * kC), "gemm_out"));
+    // MLP
+    if (rt) TRY(ln_mod<true>(h, s, h->h, h->xn, modm, off + 6 * kC, off + 7 * kC, N));
+    else TRY(ln_mod<false>(h, s, h->h, h->xn, modm, off + 6 * kC, off + 7 * kC, N));
+    TRY(gemm(h, s, EPI_GELU, h->xn, kC, w.w1, w.w1_tc, kC, N, kFF, kC, make_epi(w.b1, h->hid, kFF, rt), "gemm_fc1"));
+    TRY(gemm(h, s, EPI_RESID_GATE, h->hid, kFF, w.w2, w.w2_tc, kFF, N, kC, kFF,
+             make_epi_gate(w.b2, h->h, kC, modm, off + 8 * kC), "gemm_fc2"));
+  }
+
+  // ---------------- final layer (+ Euler update)
+  {
+    ProfScope ps(h, s, "final");
+    int off = n * 15 * kC;
+    int blocks = (int)std::min<long long>((N + 7) / 8, 148 * 8);
+    size_t smem = (size_t)D * kC * sizeof(float);
+    if (euler)
+      final_kernel<true><<<blocks, 256, smem, s>>>(h->h, modm, off, off + kC, h->w_fin, h->b_fin, D, x_in,
+                                                  h->dt, x_out, N);
+    else
+      final_kernel<false><<<blocks, 256, smem, s>>>(h->h, modm, off, off + kC, h->w_fin, h->b_fin, D, x_in,
+                                                   h->dt, x_out, N);
+    CHECK_LAUNCH(h);
+  }
+  return MDGEN_OK;
+}
+
+int prepare_call(mdgen_handle* h, cudaStream_t s, const mdgen_cond* c, int modrows) {
+  TRY(check_cond(h, c));
+  long long N = (long long)c->B * c->T * c->L;
+  bool two = !h->cfg.sim_condition && (h->cfg.tps_condition || h->cfg.inpainting);
+  TRY(ensure_workspace(h, N, (two ? 2 : 1) * (long long)c->B * c->L, modrows));
+  TRY(ensure_rope(h, s, std::max(c->T, c->L) + 1));
+  return MDGEN_OK;
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+int mdgen_abi_version(void) { return MDGEN_ABI_VERSION; }
+
+const char* mdgen_last_error(const mdgen_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int mdgen_create(const mdgen_config* cfg, mdgen_handle** out) {
+  if (!cfg || !out) { g_create_error = "null argument"; return MDGEN_E_INVALID; }
+  if (cfg->abi_version != MDGEN_ABI_VERSION) { g_create_error = "ABI version mismatch"; return MDGEN_E_INVALID; }
+  if (cfg->latent_dim != 21 && cfg->latent_dim != 28) { g_create_error = "latent_dim must be 21 or 28"; return MDGEN_E_INVALID; }
+  if (cfg->num_layers < 1 || cfg->num_layers > 16) { g_create_error = "num_layers out of range"; return MDGEN_E_INVALID; }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                     " (mdgen_b200 has no CPU fallback)";
+    return MDGEN_E_CUDA;
+  }
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, dev);
+  if (prop.major != 10) {
+    g_create_error = std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major) +
+                     std::to_string(prop.minor) + "; this library is built for sm_100a (B200) only";
+    return MDGEN_E_CUDA;
+  }
+  mdgen_handle* h = new mdgen_handle();
+  h->cfg = *cfg;
+  h->modw = cfg->num_layers * 15 * kC + 2 * kC;
+  *out = h;
+  return MDGEN_OK;
+}
+
+void mdgen_destroy(mdgen_handle* h) {
+  if (!h) return;
+  for (void* p : h->allocs) cudaFree(p);
+  for (auto& e : h->prof) { cudaEventDestroy(e.e0); cudaEventDestroy(e.e1); }
+  delete h;
+}
+
+int mdgen_set_tensor(mdgen_handle* h, const char* name, const float* data, int64_t numel) {
+  if (!h || !name || !data || numel <= 0) { if (h) h->err = "mdgen_set_tensor: bad argument"; return MDGEN_E_INVALID; }
+  RawTensor& r = h->raw[name];
+  if (r.ptr && r.numel != numel) { dev_free(h, r.ptr); r.ptr = nullptr; }
+  if (!r.ptr) TRY(dev_alloc_t(h, &r.ptr, (size_t)numel));
+  r.numel = numel;
+  CUDA_TRY(h, cudaMemcpy(r.ptr, data, (size_t)numel * sizeof(float), cudaMemcpyDeviceToDevice));
+  h->finalized = false;
+  return MDGEN_OK;
+}
+
+int mdgen_finalize_weights(mdgen_handle* h, void* stream) {
+  if (!h) return MDGEN_E_INVALID;
+  cudaStream_t s = (cudaStream_t)stream;
+  const mdgen_config& c = h->cfg;
+  const int n = c.num_layers, D = c.latent_dim;
+  const bool two_any = c.tps_condition || c.inpainting;
+  TRY(pack_new(h, s, "latent_to_emb.weight", kC, D, &h->w_lat));
+  TRY(pack_new(h, s, "latent_to_emb.bias", 1, kC, &h->b_lat));
+  TRY(pack_new(h, s, "cond_to_emb.weight", kC, D, &h->w_cond));
+  TRY(pack_new(h, s, "cond_to_emb.bias", 1, kC, &h->b_cond));
+  TRY(pack_new(h, s, "mask_to_emb.weight", 2, kC, &h->e_mask));
+  if (c.abs_pos_emb) TRY(pack_new(h, s, "pos_embed", c.crop, kC, &h->pos));
+  if (c.use_aa_emb) TRY(pack_new(h, s, "aatype_to_emb.weight", 21, kC, &h->aa_emb));
+  if (two_any) {
+    TRY(pack_new(h, s, "latent_to_emb_f.weight", kC, 7, &h->wf));
+    TRY(pack_new(h, s, "latent_to_emb_f.bias", 1, kC, &h->bf));
+    TRY(pack_new(h, s, "latent_to_emb_r.weight", kC, 7, &h->wr));
+    TRY(pack_new(h, s, "latent_to_emb_r.bias", 1, kC, &h->br));
+  }
+  TRY(pack_new(h, s, "t_embedder.mlp.0.weight", kC, kTFreq, &h->w_t0));
+  TRY(pack_new(h, s, "t_embedder.mlp.0.bias", 1, kC, &h->b_t0));
+  TRY(pack_new(h, s, "t_embedder.mlp.2.weight", kC, kC, &h->w_t2));
+  TRY(pack_new(h, s, "t_embedder.mlp.2.bias", 1, kC, &h->b_t2));
+  TRY(pack_new(h, s, "emb_to_latent.linear.weight", D, kC, &h->w_fin));
+  TRY(pack_new(h, s, "emb_to_latent.linear.bias", 1, D, &h->b_fin));
+  // concatenated adaLN table weights: [ipa 0..n-1 (6C) | main 0..n-1 (9C) | final (2C)]
+  TRY(dev_alloc_t(h, &h->w_ada, (size_t)h->modw * kC));
+  TRY(dev_alloc_t(h, &h->b_ada, (size_t)h->modw));
+  h->ipa.resize(n);
+  h->layers.resize(n);
+  for (int i = 0; i < n; ++i) {
+    std::string p = "ipa_layers." + std::to_string(i) + ".";
+    IpaLayerW& w = h->ipa[i];
+    TRY(pack(h, s, p + "adaLN_modulation.1.weight", 6 * kC, kC, h->w_ada, kC, (long long)i * 6 * kC, 1.f, 0));
+    TRY(pack(h, s, p + "adaLN_modulation.1.bias", 1, 6 * kC, h->b_ada + (size_t)i * 6 * kC, 6 * kC, 0, 1.f, 0));
+    TRY(pack_new(h, s, p + "ipa_norm.weight", 1, kC, &w.ln_g));
+    TRY(pack_new(h, s, p + "ipa_norm.bias", 1, kC, &w.ln_b));
+    TRY(pack_new(h, s, p + "ipa.head_weights", 1, kIpaH, &w.head_w));
+    TRY(dev_alloc_t(h, &w.wproj, (size_t)kIpaProj * kC));
+    TRY(dev_alloc_t(h, &w.bproj, (size_t)kIpaProj));
+    TRY(pack(h, s, p + "ipa.linear_q.weight", 128, kC, w.wproj, kC, 0, 1.f, 0));
+    TRY(pack(h, s, p + "ipa.linear_kv.weight", 256, kC, w.wproj, kC, 128, 1.f, 0));
+    TRY(pack(h, s, p + "ipa.linear_q_points.weight", 96, kC, w.wproj, kC, 384, 1.f, 0));
+    TRY(pack(h, s, p + "ipa.linear_kv_points.weight", 192, kC, w.wproj, kC, 480, 1.f, 0));
+    TRY(pack(h, s, p + "ipa.linear_q.bias", 1, 128, w.bproj, kIpaProj, 0, 1.f, 0));
+    TRY(pack(h, s, p + "ipa.linear_kv.bias", 1, 256, w.bproj + 128, kIpaProj, 0, 1.f, 0));
+    TRY(pack(h, s, p + "ipa.linear_q_points.bias", 1, 96, w.bproj + 384, kIpaProj, 0, 1.f, 0));
+    TRY(pack(h, s, p + "ipa.linear_kv_points.bias", 1, 192, w.bproj + 480, kIpaProj, 0, 1.f, 0));
+    TRY(pack_new(h, s, p + "ipa.linear_out.weight", kC, kIpaCat, &w.wout));
+    TRY(pack_new(h, s, p + "ipa.linear_out.bias", 1, kC, &w.bout));
+    TRY(pack_mha(h, s, p + "mha_l.", &w.mha));
+    TRY(pack_new(h, s, p + "fc1.weight", kFF, kC, &w.w1));
+    TRY(tc_copy(h, s, w.w1, (size_t)kFF * kC, &w.w1_tc));
+    TRY(pack_new(h, s, p + "fc1.bias", 1, kFF, &w.b1));
+    TRY(pack_new(h, s, p + "fc2.weight", kC, kFF, &w.w2));
+    TRY(tc_copy(h, s, w.w2, (size_t)kC * kFF, &w.w2_tc));
+    TRY(pack_new(h, s, p + "fc2.bias", 1, kC, &w.b2));
+  }
+  for (int i = 0; i < n; ++i) {
+    std::string p = "layers." + std::to_string(i) + ".";
+    MainLayerW& w = h->layers[i];
+    long long row0 = (long long)n * 6 * kC + (long long)i * 9 * kC;
+    TRY(pack(h, s, p + "adaLN_modulation.1.weight", 9 * kC, kC, h->w_ada, kC, row0, 1.f, 0));
+    TRY(pack(h, s, p + "adaLN_modulation.1.bias", 1, 9 * kC, h->b_ada + row0, 9 * kC, 0, 1.f, 0));
+    TRY(pack_mha(h, s, p + "mha_l.", &w.mha_l));
+    TRY(pack_mha(h, s, p + "mha_t.", &w.mha_t));
+    TRY(pack_new(h, s, p + "fc1.weight", kFF, kC, &w.w1));
+    TRY(tc_copy(h, s, w.w1, (size_t)kFF * kC, &w.w1_tc));
+    TRY(pack_new(h, s, p + "fc1.bias", 1, kFF, &w.b1));
+    TRY(pack_new(h, s, p + "fc2.weight", kC, kFF, &w.w2));
+    TRY(tc_copy(h, s, w.w2, (size_t)kC * kFF, &w.w2_tc));
+    TRY(pack_new(h, s, p + "fc2.bias", 1, kC, &w.b2));
+  }
+  {
+    long long row0 = (long long)n * 15 * kC;
+    TRY(pack(h, s, "emb_to_latent.adaLN_modulation.1.weight", 2 * kC, kC, h->w_ada, kC, row0, 1.f, 0));
+    TRY(pack(h, s, "emb_to_latent.adaLN_modulation.1.bias", 1, 2 * kC, h->b_ada + row0, 2 * kC, 0, 1.f, 0));
+  }
+  // rotary inverse frequencies: all attention modules share the same buffer values
+  TRY(pack_new(h, s, "layers.0.mha_t.attn.rot_emb.inv_freq", 1, kHalf, &h->inv_freq));
+  // timestep-embedding frequencies f_i = exp(-ln(1e4) i / 128)  (layers.py:43-45)
+  {
+    float f[128];
+    for (int i = 0; i < 128; ++i) f[i] = expf(-logf(10000.0f) * (float)i / 128.0f);
+    TRY(dev_alloc_t(h, &h->freqs, 128));
+    CUDA_TRY(h, cudaMemcpyAsync(h->freqs, f, sizeof(f), cudaMemcpyHostToDevice, s));
+  }
+  CUDA_TRY(h, cudaStreamSynchronize(s));
+  // raw copies are no longer needed
+  for (auto& kv : h->raw) dev_free(h, kv.second.ptr);
+  h->raw.clear();
+  h->rope_n = 0;
+  h->finalized = true;
+  return MDGEN_OK;
+}
+
+int mdgen_set_residue_tables(mdgen_handle* h, const float* default_frame, const float* atom14_group_pos,
+                             const int32_t* atom14_to_group, const float* atom14_mask) {
+  if (!h || !default_frame || !atom14_group_pos || !atom14_to_group || !atom14_mask) return MDGEN_E_INVALID;
+  if (!h->tb_frame) {
+    TRY(dev_alloc_t(h, &h->tb_frame, 21 * 8 * 16));
+    TRY(dev_alloc_t(h, &h->tb_pos, 21 * 14 * 3));
+    TRY(dev_alloc_t(h, &h->tb_group, 21 * 14));
+    TRY(dev_alloc_t(h, &h->tb_mask, 21 * 14));
+  }
+  CUDA_TRY(h, cudaMemcpy(h->tb_frame, default_frame, 21 * 8 * 16 * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(h, cudaMemcpy(h->tb_pos, atom14_group_pos, 21 * 14 * 3 * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(h, cudaMemcpy(h->tb_group, atom14_to_group, 21 * 14 * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(h, cudaMemcpy(h->tb_mask, atom14_mask, 21 * 14 * 4, cudaMemcpyHostToDevice));
+  return MDGEN_OK;
+}
+
+int mdgen_forward(mdgen_handle* h, const float* x, const float* t, const mdgen_cond* cond, float* out,
+                  void* stream) {
+  if (!h || !x || !t || !out) { if (h) h->err = "mdgen_forward: null argument"; return MDGEN_E_INVALID; }
+  cudaStream_t s = (cudaStream_t)stream;
+  TRY(prepare_call(h, s, cond, cond ? cond->B : 0));
+  CUDA_TRY(h, cudaMemcpyAsync(h->tvals, t, (size_t)cond->B * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  TRY(build_mod_table(h, s, cond->B));
+  TRY(build_cond(h, s, cond));
+  return run_step(h, s, cond, x, out, /*euler=*/false, nullptr, /*bstride=*/1);
+}
+
+int mdgen_sample_euler(mdgen_handle* h, const float* zs, const float* t_grid, int32_t K,
+                       const mdgen_cond* cond, float* x_out, void* stream) {
+  if (!h || !zs || !t_grid || !x_out || K < 1) { if (h) h->err = "mdgen_sample_euler: bad argument"; return MDGEN_E_INVALID; }
+  cudaStream_t s = (cudaStream_t)stream;
+  TRY(prepare_call(h, s, cond, K));
+  const long long N = (long long)cond->B * cond->T * cond->L;
+  const int D = h->cfg.latent_dim;
+  // time rows t_k (k < K) and fp32 step sizes dt_k = t_{k+1} - t_k (integrators.py:90; torchdiffeq)
+  std::vector<float> dt(K);
+  for (int k = 0; k < K; ++k) dt[k] = t_grid[k + 1] - t_grid[k];
+  CUDA_TRY(h, cudaMemcpyAsync(h->tvals, t_grid, (size_t)K * sizeof(float), cudaMemcpyHostToDevice, s));
+  CUDA_TRY(h, cudaMemcpyAsync(h->dt, dt.data(), (size_t)K * sizeof(float), cudaMemcpyHostToDevice, s));
+  CUDA_TRY(h, cudaStreamSynchronize(s));  // dt (host vector) must be consumed before it goes out of scope
+  TRY(build_mod_table(h, s, K));
+  TRY(build_cond(h, s, cond));
+  step_set_kernel<<<1, 1, 0, s>>>(h->step, 0);
+  CHECK_LAUNCH(h);
+  // ping-pong Euler state: x_k in bufA/bufB alternately; the last step writes x_out
+  const float* cur = zs;
+  float* bufA = h->xbuf;
+  float* bufB = h->xbuf2;
+  for (int k = 0; k < K; ++k) {
+    float* nxt = (k == K - 1) ? x_out : ((k & 1) == 0 ? bufA : bufB);
+    if (nxt == cur) { h->err = "internal: aliasing Euler buffers"; return MDGEN_E_INVALID; }
+    TRY(run_step(h, s, cond, cur, nxt, /*euler=*/true, h->step, /*bstride=*/0));
+    step_advance_kernel<<<1, 1, 0, s>>>(h->step);
+    CHECK_LAUNCH(h);
+    cur = nxt;
+  }
+  return MDGEN_OK;
+}
+
+int mdgen_prep_batch(mdgen_handle* h, int32_t B, int32_t T, int32_t L, const float* rots, const float* trans,
+                     const float* torsions, float* latents, float* x_cond, int64_t* x_cond_mask,
+                     void* stream) {
+  if (!h || !rots || !trans || !torsions || !latents || !x_cond || !x_cond_mask || B <= 0 || T <= 0 || L <= 0) {
+    if (h) h->err = "mdgen_prep_batch: bad argument";
+    return MDGEN_E_INVALID;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  ProfScope ps(h, s, "prep");
+  PrepFlags f;
+  f.D = h->cfg.latent_dim;
+  f.two = (h->cfg.tps_condition || h->cfg.inpainting) ? 1 : 0;
+  f.sim_condition = h->cfg.sim_condition; f.tps_condition = h->cfg.tps_condition;
+  f.inpainting = h->cfg.inpainting; f.cond_interval = h->cfg.cond_interval; f.no_torsion = h->cfg.no_torsion;
+  long long N = (long long)B * T * L;
+  prep_kernel<<<(unsigned)((N + 127) / 128), 128, 0, s>>>(rots, trans, torsions, latents, x_cond, x_cond_mask,
+                                                         B, T, L, f);
+  CHECK_LAUNCH(h);
+  return MDGEN_OK;
+}
+
+int mdgen_decode_atom14(mdgen_handle* h, int32_t B, int32_t T, int32_t L, const float* samples,
+                        const float* start_rot, const float* start_trans, const int64_t* seqres,
+                        float* atom14, void* stream) {
+  if (!h || !samples || !start_rot || !start_trans || !seqres || !atom14 || B <= 0 || T <= 0 || L <= 0) {
+    if (h) h->err = "mdgen_decode_atom14: bad argument";
+    return MDGEN_E_INVALID;
+  }
+  if (!h->tb_frame) { h->err = "residue tables not set"; return MDGEN_E_WEIGHTS; }
+  cudaStream_t s = (cudaStream_t)stream;
+  ProfScope ps(h, s, "decode");
+  ResidueTables tb{h->tb_frame, h->tb_pos, h->tb_group, h->tb_mask};
+  int tors_off = (h->cfg.tps_condition || h->cfg.inpainting) ? 14 : 7;
+  long long N = (long long)B * T * L;
+  decode_kernel<<<(unsigned)((N + 127) / 128), 128, 0, s>>>(samples, h->cfg.latent_dim, tors_off, start_rot,
+                                                           start_trans, seqres, tb, atom14, B, T, L);
+  CHECK_LAUNCH(h);
+  return MDGEN_OK;
+}
+
+int64_t mdgen_launch_count(const mdgen_handle* h) { return h ? h->launches : -1; }
+
+int mdgen_set_option(mdgen_handle* h, const char* key, int64_t value) {
+  if (!h || !key) return MDGEN_E_INVALID;
+  std::string k(key);
+  if (k == "use_tc") {
+#ifdef MDGEN_NO_TC
+    if (value) { h->err = "library built without tensor-core kernels"; return MDGEN_E_INVALID; }
+#endif
+    h->use_tc = (int)value;
+  } else if (k == "tc_min_rows") h->tc_min_rows = (int)value;
+  else if (k == "profile") {
+    h->profile = (int)value;
+    if (!value) {
+      for (auto& e : h->prof) { cudaEventDestroy(e.e0); cudaEventDestroy(e.e1); }
+      h->prof.clear();
+    }
+  } else { h->err = "unknown option " + k; return MDGEN_E_INVALID; }
+  return MDGEN_OK;
+}
+
+int64_t mdgen_get_option(const mdgen_handle* h, const char* key) {
+  if (!h || !key) return -1;
+  std::string k(key);
+  if (k == "use_tc") return h->use_tc;
+  if (k == "tc_min_rows") return h->tc_min_rows;
+  if (k == "profile") return h->profile;
+  if (k == "modw") return h->modw;
+  return -1;
+}
+
+int mdgen_profile_dump(mdgen_handle* h, char* buf, int64_t cap) {
+  if (!h || !buf || cap <= 0) return MDGEN_E_INVALID;
+  cudaDeviceSynchronize();
+  std::map<std::string, std::pair<double, long long>> acc;
+  for (auto& e : h->prof) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, e.e0, e.e1) == cudaSuccess) {
+      acc[e.name].first += ms;
+      acc[e.name].second += 1;
+    }
+    cudaEventDestroy(e.e0);
+    cudaEventDestroy(e.e1);
+  }
+  h->prof.clear();
+  std::string out;
+  for (auto& kv : acc) {
+    char line[256];
+    snprintf(line, sizeof(line), "%s %.4f %lld\n", kv.first.c_str(), kv.second.first, kv.second.second);
+    out += line;
+  }
+  snprintf(buf, (size_t)cap, "%s", out.c_str());
+  return MDGEN_OK;
+}
+
+}  // extern "C"

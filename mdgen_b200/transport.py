@@ -1,0 +1,70 @@
+"""Sampler surface of mdgen/transport/transport.py:279-451 for the one configuration the hot
+path uses (velocity prediction, GVP/Linear path => t in [0,1], mdgen/transport/transport.py:95-124,
+:560-566). `sample_ode('euler', num_steps=K+1)` returns a callable with the reference's calling
+convention `sample_fn(zs, model_fn, **model_kwargs)`; when `model_fn` is (a functools.partial of)
+our `LatentMDGenModel.forward_inference`, the whole fixed-grid Euler loop
+(mdgen/transport/integrators.py:90-113) runs natively in libmdgen_b200 and only the final state
+is produced (the reference stacks every step and the caller takes [-1], wrapper.py:444-447)."""
+from __future__ import annotations
+
+import functools
+
+import torch
+
+
+class _LastOnly:
+    """Indexable like the reference's stacked samples; only [-1] exists."""
+
+    def __init__(self, last):
+        self._last = last
+
+    def __getitem__(self, i):
+        if i != -1:
+            raise IndexError("mdgen_b200 sampler keeps only the final ODE state (index -1)")
+        return self._last
+
+
+class Sampler:
+    def __init__(self, transport=None):
+        self.transport = transport
+
+    def sample_ode(self, *, sampling_method="dopri5", num_steps=50, atol=1e-6, rtol=1e-3,
+                   reverse=False):
+        if sampling_method != "euler":
+            raise NotImplementedError(
+                "mdgen_b200: only the fixed-grid Euler sampler is native; the adaptive dopri5 "
+                "sampler is a 'next' row (SURVEY.md §8f-2)")
+        if reverse:
+            raise NotImplementedError("reverse-time sampling is not used by the hot path")
+        t_grid = torch.linspace(0.0, 1.0, num_steps)          # integrators.py:90 (t0=0, t1=1)
+
+        def sample(x, model, **model_kwargs):
+            fn, kw = model, dict(model_kwargs)
+            if isinstance(model, functools.partial):
+                fn = model.func
+                kw = {**model.keywords, **kw}
+            owner = getattr(fn, "__self__", None)
+            if owner is None or not hasattr(owner, "sample_euler"):
+                raise NotImplementedError("sample_ode needs LatentMDGenModel.forward_inference")
+            return _LastOnly(owner.sample_euler(x, t_grid, **kw))
+
+        return sample
+
+
+class Transport:
+    """Placeholder for `create_transport` (training losses are a 'next' row)."""
+
+    def __init__(self, args=None):
+        self.args = args
+        self.train_eps = 0
+        self.sample_eps = 0
+
+    def training_losses(self, *a, **k):
+        raise NotImplementedError("mdgen_b200: training path not implemented (SURVEY.md §8f-3)")
+
+
+def create_transport(args, path_type="GVP", prediction="velocity", loss_weight=None,
+                     train_eps=None, sample_eps=None):
+    if prediction != "velocity" or path_type not in ("GVP", "Linear"):
+        raise NotImplementedError("only velocity prediction with GVP/Linear paths is supported")
+    return Transport(args)
