@@ -417,7 +417,7 @@ int run_step(mdgen_handle* h, cudaStream_t s, const mdgen_cond* c, const float* 
                                                  h->wr, h->br, c->mask, T, L, h->xi, h->frot, h->ftrans,
                                                  h->fmask, BL);
     CHECK_LAUNCH(h);
-    SeqMap smi{L, rows, 1, (long long)L, 0, 1};
+    SeqMap smi{L, rows / L, 1, (long long)L, 0, 1};
     for (int i = 0; i < n; ++i) {
       const IpaLayerW& w = h->ipa[i];
       int off = i * 6 * kC;
