@@ -137,6 +137,12 @@ int64_t mdgen_get_option(const mdgen_handle* h, const char* key);
  * (name,ms,calls) triples when profiling is enabled with mdgen_set_option(h,"profile",1). */
 int mdgen_profile_dump(mdgen_handle* h, char* buf, int64_t cap);
 
+/* Test hook: out[M,N] = act(A[M,K] · W[N,K]^T + bias) through one of the library's GEMM kernels
+ * (use_tc = 1: tcgen05 TF32 kernel, operands are rounded to TF32 first; 0: fp32 SIMT kernel).
+ * act: 0 = none, 1 = erf-GELU. Lets the parity tests A/B the tensor-core kernel in isolation. */
+int mdgen_debug_linear(mdgen_handle* h, const float* A, const float* W, const float* bias, int64_t M,
+                       int32_t N, int32_t K, int32_t act, int32_t use_tc, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -20,7 +20,7 @@ EXPORTS = [
     "mdgen_create", "mdgen_destroy", "mdgen_last_error", "mdgen_set_tensor",
     "mdgen_finalize_weights", "mdgen_set_residue_tables", "mdgen_forward", "mdgen_sample_euler",
     "mdgen_prep_batch", "mdgen_decode_atom14", "mdgen_abi_version", "mdgen_launch_count",
-    "mdgen_set_option", "mdgen_get_option", "mdgen_profile_dump",
+    "mdgen_set_option", "mdgen_get_option", "mdgen_profile_dump", "mdgen_debug_linear",
 ]
 
 
@@ -75,6 +75,9 @@ def load_library():
     lib.mdgen_get_option.argtypes = [C.c_void_p, C.c_char_p]
     lib.mdgen_get_option.restype = C.c_int64
     lib.mdgen_profile_dump.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
+    lib.mdgen_debug_linear.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                       C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                       C.c_void_p]
     _lib = lib
     return lib
 
@@ -162,6 +165,18 @@ class Engine:
         for line in buf.value.decode().splitlines():
             name, ms, calls = line.split()
             out[name] = (float(ms), int(calls))
+        return out
+
+    def debug_linear(self, A, W, bias, act=0, use_tc=1):
+        """Test hook: act(A @ W.T + bias) through the library's GEMM kernels."""
+        A, W = _f32(A, "A"), _f32(W, "W")
+        b = _f32(bias, "bias") if bias is not None else None
+        M, K = A.shape
+        N = W.shape[0]
+        out = torch.empty(M, N, device=A.device, dtype=torch.float32)
+        self._check(self.lib.mdgen_debug_linear(self.h, A.data_ptr(), W.data_ptr(),
+                                                b.data_ptr() if b is not None else None, M, N, K,
+                                                int(act), int(use_tc), out.data_ptr(), _stream()))
         return out
 
     # -- calls -------------------------------------------------------------------------------

@@ -1,0 +1,373 @@
+// tcgen05 TF32 GEMM for the token-wise linear layers (QKV / out-proj / fc1 / fc2: 75 % of the
+// denoiser FLOPs):   out = epilogue( A[M,K] · W[N,K]^T + bias )      fp32 accumulate in TMEM.
+//
+// Blackwell-native structure (sm_100a only):
+//   * persistent CTAs (grid = #SMs), static round-robin tile scheduler, tiles 128 x 192, K-block
+//     32 fp32 (= one 128-byte swizzle row)
+//   * warp 0: TMA producer (cp.async.bulk.tensor.2d, SWIZZLE_128B, 5-stage mbarrier ring)
+//   * warp 1: single-thread tcgen05.mma.cta_group::1.kind::tf32 issuer, A and B from shared memory
+//     through UMMA descriptors, accumulators in TMEM (2 x 192 columns, double buffered so the
+//     epilogue of tile i overlaps the MMAs of tile i+1)
+//   * warp 2: TMEM allocator;  warps 4-7: epilogue (tcgen05.ld 32x32b -> registers -> fused
+//     bias / GELU / gate*y+residual -> 128-bit global stores)
+// Operands are fp32 bit patterns already rounded to TF32 (round-to-nearest) by their producers
+// (weights at pack time, activations by the LN / attention / GELU epilogues), so the tensor core's
+// truncation of the low 13 mantissa bits is exact.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "gemm_simt.cuh"
+
+namespace mdgen {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BN = 192;
+constexpr int TC_BK = 32;                       // fp32 elements per K-block (128 bytes)
+constexpr int TC_STAGES = 5;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
+constexpr int TC_B_BYTES = TC_BN * TC_BK * 4;   // 24 KB
+constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int TC_TMEM_COLS = 512;               // 2 accumulator buffers x 192 columns (pow2 alloc)
+
+// ---- PTX wrappers ----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem desc] · B[smem desc]^T, kind::tf32, issued by one thread
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, K-major operand, SWIZZLE_128B (cute::UMMA::SmemDescriptor):
+//   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (1: unused for swizzled K-major)
+//   [32,46) stride byte offset >> 4 (8 rows x 128 B = 1024 B between 8-row groups)
+//   [46,48) version = 1 (Blackwell) | [61,64) layout type = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t umma_desc_k128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor) for kind::tf32, fp32 accumulate, both K-major:
+//   [4,6) c_format = 1 (F32) | [7,10) a_format = 2 (TF32) | [10,13) b_format = 2 (TF32)
+//   [15] a_major = 0, [16] b_major = 0 (K) | [17,23) N >> 3 | [24,29) M >> 4
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---- vectorised epilogue on 4 consecutive columns ------------------------------------------------
+template <int MODE>
+__device__ __forceinline__ void tc_epilogue4(const Epilogue& ep, const float* gate_row, long long m, int n,
+                                             float a0, float a1, float a2, float a3) {
+  float4 v = make_float4(a0, a1, a2, a3);
+  if (ep.bias) {
+    float4 b = *reinterpret_cast<const float4*>(ep.bias + n);
+    v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+  }
+  if (MODE == EPI_GELU) { v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w); }
+  if (MODE == EPI_RESID_GATE) {
+    float4 g = *reinterpret_cast<const float4*>(gate_row + n);
+    float4 r = *reinterpret_cast<const float4*>(ep.resid + (size_t)m * ep.ldo + n);
+    v.x = r.x + g.x * v.x; v.y = r.y + g.y * v.y; v.z = r.z + g.z * v.z; v.w = r.w + g.w * v.w;
+  }
+  if (MODE == EPI_RESID) {
+    float4 r = *reinterpret_cast<const float4*>(ep.resid + (size_t)m * ep.ldo + n);
+    v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+  }
+  if (ep.round_out) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
+  *reinterpret_cast<float4*>(ep.out + (size_t)m * ep.ldo + n) = v;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                         const __grid_constant__ CUtensorMap tmB, long long M,
+                                                         int N, int K, Epilogue ep) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t sbase = (raw + 1023u) & ~1023u;          // SWIZZLE_128B tiles need 1024-B alignment
+  uint8_t* sgen = smem_raw + (sbase - raw);
+  const uint32_t bar_base = sbase + TC_STAGES * TC_STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (TC_STAGES + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * TC_STAGES + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * TC_STAGES + 2 + b); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sgen + TC_STAGES * TC_STAGE_BYTES + 8 * (2 * TC_STAGES + 4));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_blocks = N / TC_BN;
+  const long long m_blocks = (M + TC_BM - 1) / TC_BM;
+  const long long tiles = m_blocks * n_blocks;
+  const int kblocks = K / TC_BK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32((const void*)tmem_slot)), "r"((uint32_t)TC_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int m0 = (int)(tile / n_blocks) * TC_BM;
+        const int n0 = (int)(tile % n_blocks) * TC_BN;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_expect_tx(full_bar(stage), TC_STAGE_BYTES);
+          const uint32_t sa = sbase + stage * TC_STAGE_BYTES;
+          tma_load_2d(sa, &tmA, full_bar(stage), kb * TC_BK, m0);
+          tma_load_2d(sa + TC_A_BYTES, &tmB, full_bar(stage), kb * TC_BK, n0);
+          if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer (one thread) =====================
+      constexpr uint32_t idesc = umma_idesc_tf32(TC_BM, TC_BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t it = 0;
+      for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+        const uint32_t buf = it & 1u, bphase = (it >> 1) & 1u;
+        mbar_wait(tempty_bar(buf), bphase ^ 1u);           // epilogue drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + buf * TC_BN;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);               // TMA bytes have landed
+          tc_fence_after();
+          const uint32_t sa = sbase + stage * TC_STAGE_BYTES;
+          const uint64_t adesc = umma_desc_k128(sa);
+          const uint64_t bdesc = umma_desc_k128(sa + TC_A_BYTES);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 8; ++k) {
+            // advance 8 tf32 = 32 bytes along K inside the 128-byte swizzle row: +2 in 16-B units
+            tc_mma_tf32(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                        (uint32_t)((kb | k) != 0));
+          }
+          tc_commit(empty_bar(stage));                      // smem slot free once these MMAs retire
+          if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
+        }
+        tc_commit(tfull_bar(buf));                          // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue warps (TMEM -> registers -> global) =====================
+    const int q = warp & 3;                                 // TMEM lane quarter of this warp
+    const int row_in_tile = q * 32 + lane;
+    uint32_t it = 0;
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+      const uint32_t buf = it & 1u, bphase = (it >> 1) & 1u;
+      const long long m = (tile / n_blocks) * TC_BM + row_in_tile;
+      const int n0 = (int)(tile % n_blocks) * TC_BN;
+      mbar_wait(tfull_bar(buf), bphase);
+      tc_fence_after();
+      const float* gate_row = nullptr;
+      if (MODE == EPI_RESID_GATE && m < M) gate_row = mod_row(ep.mod, m) + ep.gate_off;
+#pragma unroll 1
+      for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+        uint32_t v[32];
+        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * TC_BN + c0, v);
+        tc_ld_wait();
+        if (m < M) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            tc_epilogue4<MODE>(ep, gate_row, m, n0 + c0 + 4 * j, __uint_as_float(v[4 * j]),
+                               __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                               __uint_as_float(v[4 * j + 3]));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(buf));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TC_TMEM_COLS) : "memory");
+  }
+}
+
+// ---- host side -------------------------------------------------------------------------------
+inline bool tc_gemm_supported(int N, int K) { return (N % TC_BN == 0) && (K % TC_BK == 0) && K >= TC_BK; }
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_encodeTiled get_encode_fn(std::string* err) {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !p) {
+    if (err) *err = std::string("cuTensorMapEncodeTiled unavailable: ") + cudaGetErrorString(e);
+    return nullptr;
+  }
+  fn = reinterpret_cast<PFN_encodeTiled>(p);
+  return fn;
+}
+
+// 2-D fp32 row-major [rows, cols] (leading dimension ld elements), box = [box_rows, 32 cols], SWIZZLE_128B
+inline int make_tmap_2d(CUtensorMap* map, const float* ptr, long long rows, int cols, int ld, int box_rows,
+                        std::string* err) {
+  PFN_encodeTiled fn = get_encode_fn(err);
+  if (!fn) return -2;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    if (err) *err = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r);
+    return -2;
+  }
+  return 0;
+}
+
+struct TmapCacheEntry {
+  const float* ptr; long long rows; int cols, ld, box_rows;
+  CUtensorMap map;
+};
+
+inline int get_tmap(const float* ptr, long long rows, int cols, int ld, int box_rows, CUtensorMap* out,
+                    std::string* err) {
+  static std::vector<TmapCacheEntry> cache;
+  for (auto& e : cache)
+    if (e.ptr == ptr && e.rows == rows && e.cols == cols && e.ld == ld && e.box_rows == box_rows) {
+      *out = e.map;
+      return 0;
+    }
+  TmapCacheEntry e{ptr, rows, cols, ld, box_rows, {}};
+  int rc = make_tmap_2d(&e.map, ptr, rows, cols, ld, box_rows, err);
+  if (rc) return rc;
+  if (cache.size() > 4096) cache.clear();
+  cache.push_back(e);
+  *out = e.map;
+  return 0;
+}
+
+template <int MODE>
+inline int tc_launch_mode(const CUtensorMap& ta, const CUtensorMap& tb, long long M, int N, int K,
+                          const Epilogue& ep, cudaStream_t s, int grid, std::string* err) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         TC_SMEM_BYTES);
+    if (e != cudaSuccess) {
+      if (err) *err = std::string("cudaFuncSetAttribute(gemm_tc): ") + cudaGetErrorString(e);
+      return -2;
+    }
+    configured = true;
+  }
+  gemm_tc_kernel<MODE><<<grid, 256, TC_SMEM_BYTES, s>>>(ta, tb, M, N, K, ep);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    if (err) *err = std::string("gemm_tc launch: ") + cudaGetErrorString(e);
+    return -2;
+  }
+  return 0;
+}
+
+inline int tc_gemm_launch(int mode, const float* A, int lda, const float* W, int ldw, long long M, int N, int K,
+                          const Epilogue& ep, cudaStream_t s, std::string* err) {
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  CUtensorMap ta, tb;
+  if (get_tmap(A, M, K, lda, TC_BM, &ta, err)) return -2;
+  if (get_tmap(W, N, K, ldw, TC_BN, &tb, err)) return -2;
+  long long tiles = ((M + TC_BM - 1) / TC_BM) * (N / TC_BN);
+  int grid = (int)std::min<long long>(tiles, num_sms);
+  switch (mode) {
+    case EPI_STORE: return tc_launch_mode<EPI_STORE>(ta, tb, M, N, K, ep, s, grid, err);
+    case EPI_GELU: return tc_launch_mode<EPI_GELU>(ta, tb, M, N, K, ep, s, grid, err);
+    case EPI_RESID_GATE: return tc_launch_mode<EPI_RESID_GATE>(ta, tb, M, N, K, ep, s, grid, err);
+    case EPI_RESID: return tc_launch_mode<EPI_RESID>(ta, tb, M, N, K, ep, s, grid, err);
+  }
+  if (err) *err = "bad epilogue mode";
+  return -1;
+}
+
+}  // namespace mdgen

@@ -764,6 +764,37 @@ int mdgen_decode_atom14(mdgen_handle* h, int32_t B, int32_t T, int32_t L, const 
   return MDGEN_OK;
 }
 
+int mdgen_debug_linear(mdgen_handle* h, const float* A, const float* W, const float* bias, int64_t M, int32_t N,
+                       int32_t K, int32_t act, int32_t use_tc, float* out, void* stream) {
+  if (!h || !A || !W || !out || M <= 0 || N <= 0 || K <= 0) return MDGEN_E_INVALID;
+  cudaStream_t s = (cudaStream_t)stream;
+  Epilogue ep = make_epi(bias, out, N);
+  int mode = act ? EPI_GELU : EPI_STORE;
+  if (use_tc) {
+#ifndef MDGEN_NO_TC
+    if (!tc_gemm_supported(N, K)) { h->err = "shape unsupported by the tensor-core GEMM"; return MDGEN_E_INVALID; }
+    float *Ar = nullptr, *Wr = nullptr;   // TF32-rounded operand copies
+    TRY(dev_alloc_t(h, &Ar, (size_t)M * K));
+    TRY(dev_alloc_t(h, &Wr, (size_t)N * K));
+    pack_rows_kernel<<<(unsigned)(((size_t)M * K + 255) / 256), 256, 0, s>>>(A, Ar, M, K, K, 0, 1.f, 1);
+    pack_rows_kernel<<<(unsigned)(((size_t)N * K + 255) / 256), 256, 0, s>>>(W, Wr, N, K, K, 0, 1.f, 1);
+    int rc = tc_gemm_launch(mode, Ar, K, Wr, K, M, N, K, ep, s, &h->err);
+    cudaStreamSynchronize(s);
+    dev_free(h, Ar);
+    dev_free(h, Wr);
+    return rc == 0 ? MDGEN_OK : MDGEN_E_CUDA;
+#else
+    h->err = "library built without tensor-core kernels";
+    return MDGEN_E_INVALID;
+#endif
+  }
+  int save = h->use_tc;
+  h->use_tc = 0;
+  int rc = gemm(h, s, mode, A, K, W, nullptr, K, M, N, K, ep, "debug");
+  h->use_tc = save;
+  return rc;
+}
+
 int64_t mdgen_launch_count(const mdgen_handle* h) { return h ? h->launches : -1; }
 
 int mdgen_set_option(mdgen_handle* h, const char* key, int64_t value) {

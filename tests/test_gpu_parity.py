@@ -102,3 +102,42 @@ def test_no_cpu_fallback():
     m = NewMDGenWrapper(args)
     with pytest.raises(MDGenError):
         m.model.engine()
+
+
+def _tf32(x):
+    """round-to-nearest fp32 -> tf32 (10-bit mantissa), like cvt.rna.tf32.f32"""
+    i = x.view(torch.int32)
+    i = (i + 0x1000) & ~0x1FFF
+    return i.view(torch.float32)
+
+
+@pytest.mark.parametrize("shape", [(128, 192, 32), (1000, 1152, 384), (4096, 384, 1536),
+                                   (50000, 1536, 384), (333, 384, 384)])
+@pytest.mark.parametrize("act", [0, 1])
+def test_tc_gemm_matches_fp64_of_tf32_operands(shape, act):
+    """The tcgen05 TF32 GEMM in isolation: exact products of TF32-rounded operands with fp32
+    accumulation -> compare with an fp64 matmul of the same rounded operands (tight tolerance),
+    and with the fp32 SIMT kernel on the unrounded operands (TF32 rounding tolerance)."""
+    from mdgen_b200._lib import Engine, MDGenError
+    from mdgen_b200.config import config_from_args, default_args
+    eng = Engine(config_from_args(default_args(sim_condition=True, prepend_ipa=True, abs_pos_emb=True, crop=4)))
+    M, N, K = shape
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    W = torch.randn(N, K, device="cuda", generator=g) / K ** 0.5
+    b = torch.randn(N, device="cuda", generator=g)
+    try:
+        y = eng.debug_linear(A, W, b, act=act, use_tc=1)
+    except MDGenError as e:
+        pytest.skip(str(e))
+    ref = _tf32(A).double() @ _tf32(W).double().T + b.double()
+    if act:
+        ref = torch.nn.functional.gelu(ref)
+    err = float((y.double() - ref).abs().max() / ref.abs().max())
+    assert err < 1e-5, err   # fp32 accumulation-order noise only (K up to 1536)
+    y32 = eng.debug_linear(A, W, b, act=act, use_tc=0)
+    ref32 = A.double() @ W.double().T + b.double()
+    if act:
+        ref32 = torch.nn.functional.gelu(ref32)
+    assert float((y32.double() - ref32).abs().max() / ref32.abs().max()) < 2e-6
+    assert float((y.double() - ref32).abs().max() / ref32.abs().max()) < 2e-3
