@@ -1,0 +1,340 @@
+// tcgen05 fused attention for long sequences (mha_t over T frames, mha_l over L >= 65 residues):
+// softmax(Q K^T + key-padding) V with bias-KV token and RoPE, scores never leave the SM
+// (restates mdgen/model/mha.py:260-397; K8-K13 of SURVEY.md §2c collapse into this kernel).
+//
+// One CTA = one (sequence, head); 256 threads, two CTAs per SM (the second CTA's softmax fills the
+// tensor-pipe / barrier bubbles of the first):
+//   warps 0-3  "softmax" : thread r owns query row r of the current 128-query tile == TMEM lane r.
+//                          Stages the RoPE'd, TF32-rounded Q tile, reads S from TMEM, exact online
+//                          softmax (fp32), writes P back over S in TMEM, accumulates O in registers.
+//                          Thread 0 is also the single MMA-issuing thread.
+//   warps 4-7  "loaders" : stage K (rotated) and V^T tiles of 128 keys into a 2-stage shared-memory
+//                          ring in the UMMA K-major SWIZZLE_128B layout, plus the additive key mask.
+// Per key tile:  S[128x128] = Q·K^T   (3 x tcgen05.mma kind::tf32, K = 24 = 3 x 8, A/B from smem)
+//                P = exp2(S - m)      (softmax warps, TMEM -> regs -> TMEM, in place)
+//                O_t[128x32] = P·V    (16 x tcgen05.mma kind::tf32, A = P from TMEM, B = V^T smem)
+//                acc = acc*alpha + O_t (registers; no TMEM rescale pass needed)
+// head_dim 24 is padded to 32 only in shared-memory row pitch (128-byte rows); the QK^T MMAs read
+// just the three valid 32-byte K-chunks. The softmax (MUFU ex2) is the roofline of this kernel,
+// not the tensor pipe: 96 MMA flops per score element vs. one exp.
+#pragma once
+#include "attention_simt.cuh"
+#include "gemm_tc.cuh"
+
+namespace mdgen {
+
+constexpr int AT_QT = 128;                      // queries per tile (UMMA M)
+constexpr int AT_KT = 128;                      // keys per tile (UMMA N of QK^T, K of PV)
+constexpr int AT_TILE_BYTES = 128 * 128;        // 128 rows x 128-byte pitch
+constexpr int AT_VT_BYTES = 4 * 4096;           // V^T: 4 k-atoms of [32 d-rows x 32 keys]
+constexpr int AT_STAGE_BYTES = AT_TILE_BYTES + AT_VT_BYTES;   // K + V^T
+constexpr int AT_SMEM_BYTES = 1024 /*align*/ + AT_TILE_BYTES /*Q*/ + 2 * AT_STAGE_BYTES + 2 * 512 /*kmask*/ + 128;
+constexpr int AT_TMEM_COLS = 256;               // S/P: cols [0,128), O tile: cols [128,160)
+
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+        "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+        "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
+        "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tc_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+// D[tmem] (+)= A[tmem] · B[smem desc]^T, kind::tf32
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// byte offset of 16-byte chunk `c` of row `r` inside a [rows x 128 B] K-major SWIZZLE_128B tile
+__device__ __forceinline__ uint32_t sw128_off(int r, int c) {
+  return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
+}
+
+__global__ void __launch_bounds__(256, 2) attn_tc_kernel(AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const SeqMap& sm = p.sm;
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t sbase = (raw + 1023u) & ~1023u;
+  uint8_t* sgen = smem_raw + (sbase - raw);
+  // carve-up
+  const uint32_t q_off = 0;
+  const uint32_t st_off = AT_TILE_BYTES;                       // stage s: [K 16K | V^T 16K]
+  const uint32_t km_off = AT_TILE_BYTES + 2 * AT_STAGE_BYTES;  // kmask[2][128] floats
+  const uint32_t bar_off = km_off + 2 * 512;
+  const uint32_t b_sfull = sbase + bar_off, b_ofull = b_sfull + 8;
+  auto b_kvfull = [&](int s) { return sbase + bar_off + 16 + 8 * s; };
+  auto b_kvfree = [&](int s) { return sbase + bar_off + 32 + 8 * s; };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sgen + bar_off + 48);
+  volatile int* has_mask = reinterpret_cast<volatile int*>(sgen + bar_off + 56);   // [2]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int h = blockIdx.x % kH;
+  const long long s = blockIdx.x / kH;
+  const int S = sm.S, nkeys = S + 1;
+  const int nqt = (S + AT_QT - 1) / AT_QT, nkt = (nkeys + AT_KT - 1) / AT_KT;
+
+  if (tid == 0) {
+    mbar_init(b_sfull, 1); mbar_init(b_ofull, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(b_kvfull(i), 128); mbar_init(b_kvfree(i), 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32((const void*)tmem_slot)), "r"((uint32_t)AT_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // zero the V^T rows 24..31 of both stages once (pad head-dim rows of the PV B operand)
+  for (int i = tid; i < 2 * 4 * 256; i += 256) {   // per stage: 4 atoms x 8 rows x 128 B = 4 x 256 floats
+    int st = i / 1024, rem = i % 1024, atom = rem / 256, w = rem % 256;
+    reinterpret_cast<float*>(sgen + st_off + st * AT_STAGE_BYTES + AT_TILE_BYTES + atom * 4096 + 3 * 1024)[w] = 0.f;
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
+
+  if (warp >= 4) {
+    // =============================== loaders ===============================
+    const int r = tid - 128;                       // key row inside the tile
+    for (int qt = 0, g = 0; qt < nqt; ++qt) {
+      for (int kt = 0; kt < nkt; ++kt, ++g) {
+        const int st = g & 1, use = g >> 1;
+        mbar_wait(b_kvfree(st), (uint32_t)((use & 1) ^ 1));   // PV of the previous user retired
+        uint8_t* kbase = sgen + st_off + st * AT_STAGE_BYTES;
+        uint8_t* vbase = kbase + AT_TILE_BYTES;
+        float* kmask = reinterpret_cast<float*>(sgen + km_off) + st * 128;
+        if (r == 0) has_mask[st] = 0;
+        named_bar_sync(1, 128);
+        const int j = kt * AT_KT + r;
+        float k[kHD], v[kHD];
+        float mval = 0.f;
+        if (j < S) {
+          long long tk = seq_token(sm, s, j);
+          const float4* kp = reinterpret_cast<const float4*>(p.qkv + (size_t)tk * kQKV + kC + h * kHD);
+          const float4* vp = reinterpret_cast<const float4*>(p.qkv + (size_t)tk * kQKV + 2 * kC + h * kHD);
+#pragma unroll
+          for (int i = 0; i < 6; ++i) {
+            float4 a = kp[i]; k[4*i] = a.x; k[4*i+1] = a.y; k[4*i+2] = a.z; k[4*i+3] = a.w;
+            float4 b = vp[i]; v[4*i] = b.x; v[4*i+1] = b.y; v[4*i+2] = b.z; v[4*i+3] = b.w;
+          }
+          if (p.mask && p.mask[tk] == 0.f) mval = -INFINITY;
+        } else if (j == S) {
+#pragma unroll
+          for (int i = 0; i < kHD; ++i) { k[i] = p.bias_k[h * kHD + i]; v[i] = p.bias_v[h * kHD + i]; }
+        } else {
+#pragma unroll
+          for (int i = 0; i < kHD; ++i) { k[i] = 0.f; v[i] = 0.f; }
+          mval = -INFINITY;
+        }
+        if (j <= S) rope24(k, p.cosT + j * kHalf, p.sinT + j * kHalf);
+        // K row r: 6 swizzled 16-byte chunks (24 floats), TF32-rounded
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+          float4 o = make_float4(round_tf32(k[4*c]), round_tf32(k[4*c+1]), round_tf32(k[4*c+2]), round_tf32(k[4*c+3]));
+          *reinterpret_cast<float4*>(kbase + sw128_off(r, c)) = o;
+        }
+        // V^T: element (d, key r) -> atom r/32, row d, chunk (r%32)/4, word r%4
+        {
+          uint8_t* ab = vbase + (r >> 5) * 4096;
+          const int kc = (r & 31) >> 2, kw = r & 3;
+#pragma unroll
+          for (int d = 0; d < kHD; ++d)
+            reinterpret_cast<float*>(ab + sw128_off(d, kc))[kw] = round_tf32(v[d]);
+        }
+        kmask[r] = mval;
+        if (mval != 0.f) has_mask[st] = 1;
+        fence_async_smem();                       // generic-proxy writes -> visible to the UMMA async proxy
+        mbar_arrive(b_kvfull(st));
+      }
+    }
+  } else {
+    // =============================== softmax + MMA issue ===============================
+    const int r = tid;                              // query row in tile == TMEM lane
+    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+    constexpr uint32_t idesc_qk = umma_idesc_tf32(AT_QT, AT_KT);
+    constexpr uint32_t idesc_pv = umma_idesc_tf32(AT_QT, 32);
+    const float LOG2E = 1.4426950408889634f;
+    uint32_t ph_s = 0, ph_o = 0;
+    for (int qt = 0, g = 0; qt < nqt; ++qt) {
+      // ---- stage the Q tile (all earlier MMAs reading it have completed: last o_full was waited)
+      const int e = qt * AT_QT + r;
+      const bool qok = e < S;
+      const long long tq = seq_token(sm, s, qok ? e : S - 1);
+      {
+        float q[kHD];
+        const float4* qp = reinterpret_cast<const float4*>(p.qkv + (size_t)tq * kQKV + h * kHD);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { float4 a = qp[i]; q[4*i] = a.x; q[4*i+1] = a.y; q[4*i+2] = a.z; q[4*i+3] = a.w; }
+        const int pe = qok ? e : S - 1;
+        rope24(q, p.cosT + pe * kHalf, p.sinT + pe * kHalf);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+          float4 o = make_float4(round_tf32(q[4*c] * LOG2E), round_tf32(q[4*c+1] * LOG2E),
+                                 round_tf32(q[4*c+2] * LOG2E), round_tf32(q[4*c+3] * LOG2E));
+          *reinterpret_cast<float4*>(sgen + q_off + sw128_off(r, c)) = o;
+        }
+      }
+      fence_async_smem();
+      named_bar_sync(2, 128);
+      float acc[kHD];
+#pragma unroll
+      for (int i = 0; i < kHD; ++i) acc[i] = 0.f;
+      float m_run = -INFINITY, l_run = 0.f;
+
+      auto issue_qk = [&](int gg) {
+        const int st = gg & 1, use = gg >> 1;
+        mbar_wait(b_kvfull(st), (uint32_t)(use & 1));
+        tc_fence_after();
+        const uint64_t adesc = umma_desc_k128(sbase + q_off);
+        const uint64_t bdesc = umma_desc_k128(sbase + st_off + st * AT_STAGE_BYTES);
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+          tc_mma_tf32(tmem_S, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_qk, (uint32_t)(k != 0));
+        tc_commit(b_sfull);
+      };
+      if (tid == 0) issue_qk(g);
+
+      for (int kt = 0; kt < nkt; ++kt, ++g) {
+        const int st = g & 1;
+        mbar_wait(b_sfull, ph_s); ph_s ^= 1u;
+        tc_fence_after();
+        const float* kmask = reinterpret_cast<const float*>(sgen + km_off) + st * 128;
+        const bool masked = has_mask[st] != 0;
+        // ---- pass 1: exact row max of this tile
+        float tmax = -INFINITY;
+#pragma unroll 1
+        for (int c0 = 0; c0 < AT_KT; c0 += 32) {
+          uint32_t v[32];
+          tc_ld32(tmem_S + lane_addr + c0, v);
+          tc_ld_wait();
+          if (masked) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) tmax = fmaxf(tmax, __uint_as_float(v[i]) + kmask[c0 + i]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) tmax = fmaxf(tmax, __uint_as_float(v[i]));
+          }
+        }
+        const float m_new = fmaxf(m_run, tmax);
+        const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+        const float alpha = ex2f(m_run - m_use);
+        // ---- pass 2: P = exp2(S - m) (TF32-rounded), written back over S
+        float lsum = 0.f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < AT_KT; c0 += 32) {
+          uint32_t v[32];
+          tc_ld32(tmem_S + lane_addr + c0, v);
+          tc_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float x = __uint_as_float(v[i]);
+            if (masked) x += kmask[c0 + i];
+            float pv = round_tf32(ex2f(x - m_use));
+            lsum += pv;
+            v[i] = __float_as_uint(pv);
+          }
+          tc_st32(tmem_S + lane_addr + c0, v);
+        }
+        tc_st_wait();
+        l_run = l_run * alpha + lsum;
+        m_run = m_new;
+        tc_fence_before();
+        named_bar_sync(2, 128);                      // every row's P is in TMEM
+        if (tid == 0) {
+          tc_fence_after();
+          const uint32_t vb = sbase + st_off + st * AT_STAGE_BYTES + AT_TILE_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < AT_KT / 8; ++ks) {
+            const uint64_t bdesc = umma_desc_k128(vb + (ks >> 2) * 4096 + (ks & 3) * 32);
+            tc_mma_tf32_ts(tmem_O, tmem_S + 8 * ks, bdesc, idesc_pv, (uint32_t)(ks != 0));
+          }
+          tc_commit(b_ofull);
+          tc_commit(b_kvfree(st));                   // K/V stage reusable once the PV MMAs retire
+          if (kt + 1 < nkt) issue_qk(g + 1);         // next S (in order after PV on the tensor pipe)
+        }
+        // ---- O tile -> registers
+        mbar_wait(b_ofull, ph_o); ph_o ^= 1u;
+        tc_fence_after();
+        {
+          uint32_t o0[8], o1[8], o2[8];
+          tc_ld8(tmem_O + lane_addr + 0, o0);
+          tc_ld8(tmem_O + lane_addr + 8, o1);
+          tc_ld8(tmem_O + lane_addr + 16, o2);
+          tc_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            acc[i] = fmaf(acc[i], alpha, __uint_as_float(o0[i]));
+            acc[8 + i] = fmaf(acc[8 + i], alpha, __uint_as_float(o1[i]));
+            acc[16 + i] = fmaf(acc[16 + i], alpha, __uint_as_float(o2[i]));
+          }
+        }
+        tc_fence_before();
+      }
+      // ---- write this query tile's output rows
+      if (qok) {
+        const float inv = 1.0f / l_run;
+        float4* op = reinterpret_cast<float4*>(p.out + (size_t)tq * kC + h * kHD);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          float4 o = make_float4(acc[4*i] * inv, acc[4*i+1] * inv, acc[4*i+2] * inv, acc[4*i+3] * inv);
+          if (p.round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+          op[i] = o;
+        }
+      }
+      named_bar_sync(2, 128);   // all rows done with TMEM O / smem Q before the next tile restages Q
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)AT_TMEM_COLS) : "memory");
+  }
+}
+
+inline int attn_tc_launch(const AttnParams& p, cudaStream_t s, std::string* err) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES);
+    if (e != cudaSuccess) {
+      if (err) *err = std::string("cudaFuncSetAttribute(attn_tc): ") + cudaGetErrorString(e);
+      return -2;
+    }
+    configured = true;
+  }
+  long long blocks = p.sm.num_seq * kH;
+  attn_tc_kernel<<<(unsigned)blocks, 256, AT_SMEM_BYTES, s>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    if (err) *err = std::string("attn_tc launch: ") + cudaGetErrorString(e);
+    return -2;
+  }
+  return 0;
+}
+
+}  // namespace mdgen

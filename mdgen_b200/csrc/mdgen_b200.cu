@@ -18,6 +18,7 @@
 #include "ipa.cuh"
 #ifndef MDGEN_NO_TC
 #include "gemm_tc.cuh"
+#include "attention_tc.cuh"
 #endif
 
 using namespace mdgen;
@@ -66,6 +67,7 @@ struct mdgen_handle {
 #else
   int use_tc = 1;      // tcgen05 TF32 GEMMs for the token GEMMs (0 = fp32 SIMT validation path)
 #endif
+  int use_tc_attn = 1; // tcgen05 attention for sequences longer than 64 (needs use_tc)
   int tc_min_rows = 1024;  // below this many rows the SIMT GEMM is used (latency-bound shapes)
   int profile = 0;
   std::vector<ProfEntry> prof;
@@ -333,6 +335,13 @@ int attention(mdgen_handle* h, cudaStream_t s, const float* qkv, const float* ma
   AttnParams p;
   p.qkv = qkv; p.mask = mask; p.bias_k = w.bias_k; p.bias_v = w.bias_v;
   p.cosT = h->cosT; p.sinT = h->sinT; p.out = out; p.round_out = round_out; p.sm = sm;
+#ifndef MDGEN_NO_TC
+  if (h->use_tc && h->use_tc_attn && sm.S > 64) {
+    if (attn_tc_launch(p, s, &h->err)) return MDGEN_E_CUDA;
+    h->launches++;
+    return MDGEN_OK;
+  }
+#endif
   if (sm.S <= 64) {
     long long total = sm.num_seq * sm.S * kH;
     attn_small_kernel<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(p);
@@ -806,6 +815,7 @@ int mdgen_set_option(mdgen_handle* h, const char* key, int64_t value) {
 #endif
     h->use_tc = (int)value;
   } else if (k == "tc_min_rows") h->tc_min_rows = (int)value;
+  else if (k == "use_tc_attn") h->use_tc_attn = (int)value;
   else if (k == "profile") {
     h->profile = (int)value;
     if (!value) {
@@ -821,6 +831,7 @@ int64_t mdgen_get_option(const mdgen_handle* h, const char* key) {
   std::string k(key);
   if (k == "use_tc") return h->use_tc;
   if (k == "tc_min_rows") return h->tc_min_rows;
+  if (k == "use_tc_attn") return h->use_tc_attn;
   if (k == "profile") return h->profile;
   if (k == "modw") return h->modw;
   return -1;
