@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(128) attn_small_kernel(AttnParams p) {
 #pragma unroll
   for (int i = 0; i < 6; ++i) {
     float4 o = make_float4(acc[4*i] * inv, acc[4*i+1] * inv, acc[4*i+2] * inv, acc[4*i+3] * inv);
-    if (p.round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+    if (p.round_out) { o.x = round_tf32_fast(o.x); o.y = round_tf32_fast(o.y); o.z = round_tf32_fast(o.z); o.w = round_tf32_fast(o.w); }
     op[i] = o;
   }
 }
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(128) attn_flash_simt_kernel(AttnParams p) {
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
       float4 o = make_float4(acc[u][4*i] * inv, acc[u][4*i+1] * inv, acc[u][4*i+2] * inv, acc[u][4*i+3] * inv);
-      if (p.round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+      if (p.round_out) { o.x = round_tf32_fast(o.x); o.y = round_tf32_fast(o.y); o.z = round_tf32_fast(o.z); o.w = round_tf32_fast(o.w); }
       op[i] = o;
     }
   }

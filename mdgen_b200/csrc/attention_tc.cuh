@@ -8,8 +8,11 @@
 //                          Stages the RoPE'd, TF32-rounded Q tile, reads S from TMEM, exact online
 //                          softmax (fp32), writes P back over S in TMEM, accumulates O in registers.
 //                          Thread 0 is also the single MMA-issuing thread.
-//   warps 4-7  "loaders" : stage K (rotated) and V^T tiles of 128 keys into a 2-stage shared-memory
-//                          ring in the UMMA K-major SWIZZLE_128B layout, plus the additive key mask.
+//   prologue (all warps) : builds, once per (sequence, head), the UMMA-ready images of every key tile
+//                          (K rotated by RoPE, V transposed, both TF32-rounded, K-major SWIZZLE_128B,
+//                          plus the additive key mask) in an L2-resident global scratch.
+//   warp 4 lane 0        : producer - one cp.async.bulk (TMA 1-D) per key tile refills a 2-stage
+//                          shared-memory ring from that scratch for each of the query tiles.
 // Per key tile:  S[128x128] = Q·K^T   (3 x tcgen05.mma kind::tf32, K = 24 = 3 x 8, A/B from smem)
 //                P = exp2(S - m)      (softmax warps, TMEM -> regs -> TMEM, in place)
 //                O_t[128x32] = P·V    (16 x tcgen05.mma kind::tf32, A = P from TMEM, B = V^T smem)
@@ -27,8 +30,10 @@ constexpr int AT_QT = 128;                      // queries per tile (UMMA M)
 constexpr int AT_KT = 128;                      // keys per tile (UMMA N of QK^T, K of PV)
 constexpr int AT_TILE_BYTES = 128 * 128;        // 128 rows x 128-byte pitch
 constexpr int AT_VT_BYTES = 4 * 4096;           // V^T: 4 k-atoms of [32 d-rows x 32 keys]
-constexpr int AT_STAGE_BYTES = AT_TILE_BYTES + AT_VT_BYTES;   // K + V^T
-constexpr int AT_SMEM_BYTES = 1024 /*align*/ + AT_TILE_BYTES /*Q*/ + 2 * AT_STAGE_BYTES + 2 * 512 /*kmask*/ + 128;
+constexpr int AT_KM_BYTES = 512 + 16;            // additive key mask (128 floats) + "tile has masked keys" flag
+constexpr int AT_IMG_BYTES = AT_TILE_BYTES + AT_VT_BYTES + AT_KM_BYTES;   // one staged key tile: K | V^T | mask
+constexpr int AT_STAGE_BYTES = 34 * 1024;       // smem stage pitch (keeps K / V^T 1024-byte aligned)
+constexpr int AT_SMEM_BYTES = 1024 /*align*/ + AT_TILE_BYTES /*Q*/ + 2 * AT_STAGE_BYTES + 128;
 constexpr int AT_TMEM_COLS = 256;               // S/P: cols [0,128), O tile: cols [128,160)
 
 __device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&v)[32]) {
@@ -48,6 +53,23 @@ __device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t (&v)[8]) {
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                : "r"(taddr)
                : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+        "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
 }
 // D[tmem] (+)= A[tmem] · B[smem desc]^T, kind::tf32
 __device__ __forceinline__ void tc_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
@@ -69,12 +91,29 @@ __device__ __forceinline__ float ex2f(float x) {
   return y;
 }
 
+// mbarrier wait with a nanosleep back-off: used by the loader warps so their polling does not
+// steal issue slots from the softmax warps sharing the SM sub-partitions.
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  for (;;) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) break;
+    __nanosleep(256);
+  }
+}
+
 // byte offset of 16-byte chunk `c` of row `r` inside a [rows x 128 B] K-major SWIZZLE_128B tile
 __device__ __forceinline__ uint32_t sw128_off(int r, int c) {
   return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
 }
 
-__global__ void __launch_bounds__(256, 2) attn_tc_kernel(AttnParams p) {
+__global__ void __launch_bounds__(256, 2) attn_tc_kernel(AttnParams p, uint8_t* __restrict__ scratch) {
   extern __shared__ uint8_t smem_raw[];
   const SeqMap& sm = p.sm;
   const uint32_t raw = smem_u32(smem_raw);
@@ -82,24 +121,23 @@ __global__ void __launch_bounds__(256, 2) attn_tc_kernel(AttnParams p) {
   uint8_t* sgen = smem_raw + (sbase - raw);
   // carve-up
   const uint32_t q_off = 0;
-  const uint32_t st_off = AT_TILE_BYTES;                       // stage s: [K 16K | V^T 16K]
-  const uint32_t km_off = AT_TILE_BYTES + 2 * AT_STAGE_BYTES;  // kmask[2][128] floats
-  const uint32_t bar_off = km_off + 2 * 512;
+  const uint32_t st_off = AT_TILE_BYTES;                       // stage s: [K 16K | V^T 16K | kmask+flag]
+  const uint32_t bar_off = AT_TILE_BYTES + 2 * AT_STAGE_BYTES;
   const uint32_t b_sfull = sbase + bar_off, b_ofull = b_sfull + 8;
   auto b_kvfull = [&](int s) { return sbase + bar_off + 16 + 8 * s; };
   auto b_kvfree = [&](int s) { return sbase + bar_off + 32 + 8 * s; };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sgen + bar_off + 48);
-  volatile int* has_mask = reinterpret_cast<volatile int*>(sgen + bar_off + 56);   // [2]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int h = blockIdx.x % kH;
   const long long s = blockIdx.x / kH;
   const int S = sm.S, nkeys = S + 1;
   const int nqt = (S + AT_QT - 1) / AT_QT, nkt = (nkeys + AT_KT - 1) / AT_KT;
+  uint8_t* img = scratch + (size_t)blockIdx.x * nkt * AT_IMG_BYTES;   // this CTA's key-tile images
 
   if (tid == 0) {
     mbar_init(b_sfull, 1); mbar_init(b_ofull, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(b_kvfull(i), 128); mbar_init(b_kvfree(i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(b_kvfull(i), 1); mbar_init(b_kvfree(i), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -107,73 +145,77 @@ __global__ void __launch_bounds__(256, 2) attn_tc_kernel(AttnParams p) {
                  ::"r"(smem_u32((const void*)tmem_slot)), "r"((uint32_t)AT_TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  // zero the V^T rows 24..31 of both stages once (pad head-dim rows of the PV B operand)
-  for (int i = tid; i < 2 * 4 * 256; i += 256) {   // per stage: 4 atoms x 8 rows x 128 B = 4 x 256 floats
-    int st = i / 1024, rem = i % 1024, atom = rem / 256, w = rem % 256;
-    reinterpret_cast<float*>(sgen + st_off + st * AT_STAGE_BYTES + AT_TILE_BYTES + atom * 4096 + 3 * 1024)[w] = 0.f;
+  // =============================== prologue: key-tile images ===============================
+  // (rows 24..31 of every V^T atom are never written: the scratch is zero-filled at allocation)
+  for (int j = tid; j < nkt * AT_KT; j += 256) {
+    const int kt = j >> 7, r = j & 127;
+    uint8_t* kbase = img + (size_t)kt * AT_IMG_BYTES;
+    uint8_t* vbase = kbase + AT_TILE_BYTES;
+    float* kmask = reinterpret_cast<float*>(vbase + AT_VT_BYTES);
+    float k[kHD], v[kHD];
+    float mval = 0.f;
+    if (j < S) {
+      long long tk = seq_token(sm, s, j);
+      const float4* kp = reinterpret_cast<const float4*>(p.qkv + (size_t)tk * kQKV + kC + h * kHD);
+      const float4* vp = reinterpret_cast<const float4*>(p.qkv + (size_t)tk * kQKV + 2 * kC + h * kHD);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        float4 a = kp[i]; k[4*i] = a.x; k[4*i+1] = a.y; k[4*i+2] = a.z; k[4*i+3] = a.w;
+        float4 b = vp[i]; v[4*i] = b.x; v[4*i+1] = b.y; v[4*i+2] = b.z; v[4*i+3] = b.w;
+      }
+      if (p.mask && p.mask[tk] == 0.f) mval = -INFINITY;
+    } else if (j == S) {
+#pragma unroll
+      for (int i = 0; i < kHD; ++i) { k[i] = p.bias_k[h * kHD + i]; v[i] = p.bias_v[h * kHD + i]; }
+    } else {
+#pragma unroll
+      for (int i = 0; i < kHD; ++i) { k[i] = 0.f; v[i] = 0.f; }
+      mval = -INFINITY;
+    }
+    if (j <= S) rope24(k, p.cosT + j * kHalf, p.sinT + j * kHalf);
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      float4 o = make_float4(round_tf32_fast(k[4*c]), round_tf32_fast(k[4*c+1]), round_tf32_fast(k[4*c+2]), round_tf32_fast(k[4*c+3]));
+      *reinterpret_cast<float4*>(kbase + sw128_off(r, c)) = o;
+    }
+    {
+      uint8_t* ab = vbase + (r >> 5) * 4096;
+      const int kc = (r & 31) >> 2, kw = r & 3;
+#pragma unroll
+      for (int d = 0; d < kHD; ++d)
+        reinterpret_cast<float*>(ab + sw128_off(d, kc))[kw] = round_tf32_fast(v[d]);
+    }
+    kmask[r] = mval;
+    // per-slice flag (ints 128..131 of the mask block): any masked / out-of-range key among the
+    // 32 keys this warp just wrote
+    const unsigned any = __ballot_sync(0xffffffffu, mval != 0.f);
+    if (lane == 0) reinterpret_cast<int*>(kmask + 128)[r >> 5] = any ? 1 : 0;
   }
-  fence_async_smem();
+  asm volatile("fence.proxy.async;" ::: "memory");             // generic global writes -> async-proxy (bulk copy) reads
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
 
-  if (warp >= 4) {
-    // =============================== loaders ===============================
-    const int r = tid - 128;                       // key row inside the tile
-    for (int qt = 0, g = 0; qt < nqt; ++qt) {
-      for (int kt = 0; kt < nkt; ++kt, ++g) {
-        const int st = g & 1, use = g >> 1;
-        mbar_wait(b_kvfree(st), (uint32_t)((use & 1) ^ 1));   // PV of the previous user retired
-        uint8_t* kbase = sgen + st_off + st * AT_STAGE_BYTES;
-        uint8_t* vbase = kbase + AT_TILE_BYTES;
-        float* kmask = reinterpret_cast<float*>(sgen + km_off) + st * 128;
-        if (r == 0) has_mask[st] = 0;
-        named_bar_sync(1, 128);
-        const int j = kt * AT_KT + r;
-        float k[kHD], v[kHD];
-        float mval = 0.f;
-        if (j < S) {
-          long long tk = seq_token(sm, s, j);
-          const float4* kp = reinterpret_cast<const float4*>(p.qkv + (size_t)tk * kQKV + kC + h * kHD);
-          const float4* vp = reinterpret_cast<const float4*>(p.qkv + (size_t)tk * kQKV + 2 * kC + h * kHD);
-#pragma unroll
-          for (int i = 0; i < 6; ++i) {
-            float4 a = kp[i]; k[4*i] = a.x; k[4*i+1] = a.y; k[4*i+2] = a.z; k[4*i+3] = a.w;
-            float4 b = vp[i]; v[4*i] = b.x; v[4*i+1] = b.y; v[4*i+2] = b.z; v[4*i+3] = b.w;
-          }
-          if (p.mask && p.mask[tk] == 0.f) mval = -INFINITY;
-        } else if (j == S) {
-#pragma unroll
-          for (int i = 0; i < kHD; ++i) { k[i] = p.bias_k[h * kHD + i]; v[i] = p.bias_v[h * kHD + i]; }
-        } else {
-#pragma unroll
-          for (int i = 0; i < kHD; ++i) { k[i] = 0.f; v[i] = 0.f; }
-          mval = -INFINITY;
+  if (warp == 4) {
+    if (lane == 0) {
+      // =============================== producer (TMA 1-D bulk copies) ===============================
+      for (int qt = 0, g = 0; qt < nqt; ++qt) {
+        for (int kt = 0; kt < nkt; ++kt, ++g) {
+          const int st = g & 1, use = g >> 1;
+          mbar_wait_backoff(b_kvfree(st), (uint32_t)((use & 1) ^ 1));   // PV of the previous user retired
+          mbar_expect_tx(b_kvfull(st), AT_IMG_BYTES);
+          const uint32_t dst = sbase + st_off + st * AT_STAGE_BYTES;
+          const uint8_t* src = img + (size_t)kt * AT_IMG_BYTES;
+          asm volatile(
+              "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+              ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"((uint32_t)AT_IMG_BYTES), "r"(b_kvfull(st))
+              : "memory");
         }
-        if (j <= S) rope24(k, p.cosT + j * kHalf, p.sinT + j * kHalf);
-        // K row r: 6 swizzled 16-byte chunks (24 floats), TF32-rounded
-#pragma unroll
-        for (int c = 0; c < 6; ++c) {
-          float4 o = make_float4(round_tf32(k[4*c]), round_tf32(k[4*c+1]), round_tf32(k[4*c+2]), round_tf32(k[4*c+3]));
-          *reinterpret_cast<float4*>(kbase + sw128_off(r, c)) = o;
-        }
-        // V^T: element (d, key r) -> atom r/32, row d, chunk (r%32)/4, word r%4
-        {
-          uint8_t* ab = vbase + (r >> 5) * 4096;
-          const int kc = (r & 31) >> 2, kw = r & 3;
-#pragma unroll
-          for (int d = 0; d < kHD; ++d)
-            reinterpret_cast<float*>(ab + sw128_off(d, kc))[kw] = round_tf32(v[d]);
-        }
-        kmask[r] = mval;
-        if (mval != 0.f) has_mask[st] = 1;
-        fence_async_smem();                       // generic-proxy writes -> visible to the UMMA async proxy
-        mbar_arrive(b_kvfull(st));
       }
     }
-  } else {
+  } else if (warp < 4) {
     // =============================== softmax + MMA issue ===============================
     const int r = tid;                              // query row in tile == TMEM lane
     const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
@@ -195,8 +237,8 @@ __global__ void __launch_bounds__(256, 2) attn_tc_kernel(AttnParams p) {
         rope24(q, p.cosT + pe * kHalf, p.sinT + pe * kHalf);
 #pragma unroll
         for (int c = 0; c < 6; ++c) {
-          float4 o = make_float4(round_tf32(q[4*c] * LOG2E), round_tf32(q[4*c+1] * LOG2E),
-                                 round_tf32(q[4*c+2] * LOG2E), round_tf32(q[4*c+3] * LOG2E));
+          float4 o = make_float4(round_tf32_fast(q[4*c] * LOG2E), round_tf32_fast(q[4*c+1] * LOG2E),
+                                 round_tf32_fast(q[4*c+2] * LOG2E), round_tf32_fast(q[4*c+3] * LOG2E));
           *reinterpret_cast<float4*>(sgen + q_off + sw128_off(r, c)) = o;
         }
       }
@@ -224,42 +266,57 @@ __global__ void __launch_bounds__(256, 2) attn_tc_kernel(AttnParams p) {
         const int st = g & 1;
         mbar_wait(b_sfull, ph_s); ph_s ^= 1u;
         tc_fence_after();
-        const float* kmask = reinterpret_cast<const float*>(sgen + km_off) + st * 128;
-        const bool masked = has_mask[st] != 0;
-        // ---- pass 1: exact row max of this tile
+        const float* kmask = reinterpret_cast<const float*>(sgen + st_off + st * AT_STAGE_BYTES + AT_TILE_BYTES + AT_VT_BYTES);
+        const int4 fl = *reinterpret_cast<const int4*>(kmask + 128);   // one flag per 32-key slice
+        const bool masked = (fl.x | fl.y | fl.z | fl.w) != 0;
+        // ---- pass 1: exact row max of this tile (chunk c+1 is in flight while chunk c is reduced)
         float tmax = -INFINITY;
-#pragma unroll 1
-        for (int c0 = 0; c0 < AT_KT; c0 += 32) {
-          uint32_t v[32];
-          tc_ld32(tmem_S + lane_addr + c0, v);
+        {
+          uint32_t va[16], vb[16];
+          tc_ld16(tmem_S + lane_addr, va);
           tc_ld_wait();
-          if (masked) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) tmax = fmaxf(tmax, __uint_as_float(v[i]) + kmask[c0 + i]);
-          } else {
+          for (int cc = 0; cc < 8; ++cc) {
+            uint32_t (&cur)[16] = (cc & 1) ? vb : va;
+            uint32_t (&nxt)[16] = (cc & 1) ? va : vb;
+            if (cc < 7) tc_ld16(tmem_S + lane_addr + (cc + 1) * 16, nxt);
+            if (masked) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) tmax = fmaxf(tmax, __uint_as_float(v[i]));
+              for (int i = 0; i < 16; ++i) tmax = fmaxf(tmax, __uint_as_float(cur[i]) + kmask[cc * 16 + i]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) tmax = fmaxf(tmax, __uint_as_float(cur[i]));
+            }
+            if (cc < 7) tc_ld_wait();
           }
         }
         const float m_new = fmaxf(m_run, tmax);
         const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
         const float alpha = ex2f(m_run - m_use);
-        // ---- pass 2: P = exp2(S - m) (TF32-rounded), written back over S
+        // ---- pass 2: P = exp2(S - m), written back over S. The denominator sums the exact fp32 p;
+        // the numerator operand is rounded to TF32 by adding half an ulp (the MMA truncates the low
+        // 13 mantissa bits), so its rounding error is zero-mean.
         float lsum = 0.f;
-#pragma unroll 1
-        for (int c0 = 0; c0 < AT_KT; c0 += 32) {
-          uint32_t v[32];
-          tc_ld32(tmem_S + lane_addr + c0, v);
+        {
+          uint32_t va[16], vb[16];
+          tc_ld16(tmem_S + lane_addr, va);
           tc_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float x = __uint_as_float(v[i]);
-            if (masked) x += kmask[c0 + i];
-            float pv = round_tf32(ex2f(x - m_use));
-            lsum += pv;
-            v[i] = __float_as_uint(pv);
+          for (int cc = 0; cc < 8; ++cc) {
+            uint32_t (&cur)[16] = (cc & 1) ? vb : va;
+            uint32_t (&nxt)[16] = (cc & 1) ? va : vb;
+            if (cc < 7) tc_ld16(tmem_S + lane_addr + (cc + 1) * 16, nxt);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float x = __uint_as_float(cur[i]);
+              if (masked) x += kmask[cc * 16 + i];
+              float pv = ex2f(x - m_use);
+              lsum += pv;
+              cur[i] = __float_as_uint(pv) + 0x1000u;
+            }
+            if (cc < 7) tc_ld_wait();
+            tc_st16(tmem_S + lane_addr + cc * 16, cur);
           }
-          tc_st32(tmem_S + lane_addr + c0, v);
         }
         tc_st_wait();
         l_run = l_run * alpha + lsum;
@@ -303,7 +360,7 @@ __global__ void __launch_bounds__(256, 2) attn_tc_kernel(AttnParams p) {
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
           float4 o = make_float4(acc[4*i] * inv, acc[4*i+1] * inv, acc[4*i+2] * inv, acc[4*i+3] * inv);
-          if (p.round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+          if (p.round_out) { o.x = round_tf32_fast(o.x); o.y = round_tf32_fast(o.y); o.z = round_tf32_fast(o.z); o.w = round_tf32_fast(o.w); }
           op[i] = o;
         }
       }
@@ -317,7 +374,13 @@ __global__ void __launch_bounds__(256, 2) attn_tc_kernel(AttnParams p) {
   }
 }
 
-inline int attn_tc_launch(const AttnParams& p, cudaStream_t s, std::string* err) {
+// bytes of global scratch the kernel needs for this launch (zero-filled once at allocation)
+inline size_t attn_tc_scratch_bytes(const SeqMap& sm) {
+  const int nkt = (sm.S + 1 + AT_KT - 1) / AT_KT;
+  return (size_t)sm.num_seq * kH * nkt * AT_IMG_BYTES;
+}
+
+inline int attn_tc_launch(const AttnParams& p, uint8_t* scratch, cudaStream_t s, std::string* err) {
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES);
@@ -328,7 +391,7 @@ inline int attn_tc_launch(const AttnParams& p, cudaStream_t s, std::string* err)
     configured = true;
   }
   long long blocks = p.sm.num_seq * kH;
-  attn_tc_kernel<<<(unsigned)blocks, 256, AT_SMEM_BYTES, s>>>(p);
+  attn_tc_kernel<<<(unsigned)blocks, 256, AT_SMEM_BYTES, s>>>(p, scratch);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     if (err) *err = std::string("attn_tc launch: ") + cudaGetErrorString(e);

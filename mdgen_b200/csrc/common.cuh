@@ -14,7 +14,8 @@ constexpr int kHalf = 12;      // rotary half
 constexpr int kFF = 1536;      // ffn dim
 constexpr int kQKV = 3 * kC;   // packed q|k|v projection width
 constexpr int kIpaH = 4, kIpaC = 32, kIpaPq = 8, kIpaPv = 8;
-constexpr int kIpaProj = 128 + 256 + 96 + 192;  // q | kv | q_pts | kv_pts = 672
+constexpr int kIpaProjUsed = 128 + 256 + 96 + 192;  // q | kv | q_pts | kv_pts = 672
+constexpr int kIpaProj = 768;  // row pitch of the fused projection (padded to a tensor-core N tile multiple)
 constexpr int kIpaCat = kIpaH * (kIpaC + 4 * kIpaPv);  // 256
 constexpr int kTFreq = 256;
 
@@ -52,9 +53,12 @@ __device__ __forceinline__ float warp_max(float v) {
 // of letting the MMA truncate.
 __device__ __forceinline__ float round_tf32(float x) {
   uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));   // (emulated with ~4 integer ops on sm_100a)
   return __uint_as_float(u);
 }
+// One-instruction variant for activations that only feed a tensor-core MMA: add half a TF32 ulp to
+// the magnitude; the MMA's truncation of the low 13 bits completes the round-to-nearest.
+__device__ __forceinline__ float round_tf32_fast(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }
 
 __device__ __forceinline__ float gelu_erf(float x) {  // mdgen/model/layers.py:77-84
   return x * 0.5f * (1.0f + erff(x * 0.70710678118654752440f));

@@ -80,7 +80,7 @@ __global__ void ln_mod_kernel(const float* __restrict__ x, float* __restrict__ y
     o.y = (v[i].y - mean) * rstd * (1.0f + b.y) + a.y;
     o.z = (v[i].z - mean) * rstd * (1.0f + b.z) + a.z;
     o.w = (v[i].w - mean) * rstd * (1.0f + b.w) + a.w;
-    if (ROUND) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+    if (ROUND) { o.x = round_tf32_fast(o.x); o.y = round_tf32_fast(o.y); o.z = round_tf32_fast(o.z); o.w = round_tf32_fast(o.w); }
     yr[i * 32 + lane] = o;
   }
 }
@@ -118,7 +118,7 @@ __global__ void ln_affine_kernel(const float* __restrict__ x, float* __restrict_
     o.y = (v[i].y - mean) * rstd * a.y + b.y;
     o.z = (v[i].z - mean) * rstd * a.z + b.z;
     o.w = (v[i].w - mean) * rstd * a.w + b.w;
-    if (ROUND) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+    if (ROUND) { o.x = round_tf32_fast(o.x); o.y = round_tf32_fast(o.y); o.z = round_tf32_fast(o.z); o.w = round_tf32_fast(o.w); }
     yr[i * 32 + lane] = o;
   }
 }

@@ -33,7 +33,7 @@ __device__ __forceinline__ float apply_epilogue(const Epilogue& ep, float acc, l
     v = ep.resid[(size_t)m * ep.ldo + n] + mr[ep.gate_off + n] * v;
   }
   if (MODE == EPI_RESID) v = ep.resid[(size_t)m * ep.ldo + n] + v;
-  if (ep.round_out) v = round_tf32(v);
+  if (ep.round_out) v = round_tf32_fast(v);
   return v;
 }
 
@@ -107,6 +107,95 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const float* __restrict_
     for (int j = 0; j < 8; ++j) {
       int n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
       if (n < N) ep.out[(size_t)m * ep.ldo + n] = apply_epilogue<MODE>(ep, acc[i][j], m, n);
+    }
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// "Skinny" fp32 GEMM for the key-frame (IPA) trunk: M = B*L rows only (256 at BASELINE configs 2/5),
+// so the kernel is latency- not throughput-bound. 32 x 64 tiles (many CTAs even for M = 256) and a
+// 3-stage cp.async pipeline keep several K-tiles in flight per CTA. Exact fp32 FMA arithmetic: the
+// trunk output is broadcast-added to every frame, so its rounding error is coherent across the whole
+// trajectory (measured: TF32 here costs 40x more final-state error than TF32 in the token GEMMs).
+// Requirements: N % 64 == 0, K % 32 == 0, lda/ldw % 4 == 0 (16-byte aligned rows).
+constexpr int SK_BM = 32, SK_BN = 64, SK_BK = 32, SK_PITCH = 36, SK_STAGES = 3;
+constexpr int SK_SMEM_BYTES = SK_STAGES * (SK_BM + SK_BN) * SK_PITCH * 4;
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(128) gemm_skinny_kernel(const float* __restrict__ A, int lda,
+                                                          const float* __restrict__ W, int ldw,
+                                                          long long M, int N, int K, Epilogue ep) {
+  extern __shared__ __align__(16) float sk_smem[];
+  float* As = sk_smem;                                       // [stage][32][36]
+  float* Ws = sk_smem + SK_STAGES * SK_BM * SK_PITCH;        // [stage][64][36]
+  const int tid = threadIdx.x;
+  const long long m0 = (long long)blockIdx.x * SK_BM;
+  const int n0 = blockIdx.y * SK_BN;
+  const int ty = tid >> 4, tx = tid & 15;
+  const int nk = K / SK_BK;
+  auto load_tile = [&](int kt, int stage) {
+    const int k0 = kt * SK_BK;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {                            // A: 32 rows x 8 chunks
+      int c = tid + i * 128, row = c >> 3, ch = c & 7;
+      long long m = min(m0 + row, M - 1);
+      cp_async16(As + (stage * SK_BM + row) * SK_PITCH + ch * 4, A + (size_t)m * lda + k0 + ch * 4);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {                            // W: 64 rows x 8 chunks
+      int c = tid + i * 128, row = c >> 3, ch = c & 7;
+      cp_async16(Ws + (stage * SK_BN + row) * SK_PITCH + ch * 4, W + (size_t)(n0 + row) * ldw + k0 + ch * 4);
+    }
+  };
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll
+  for (int s = 0; s < SK_STAGES - 1; ++s) {
+    if (s < nk) load_tile(s, s);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  for (int kt = 0; kt < nk; ++kt) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(SK_STAGES - 2) : "memory");
+    __syncthreads();
+    if (kt + SK_STAGES - 1 < nk) load_tile(kt + SK_STAGES - 1, (kt + SK_STAGES - 1) % SK_STAGES);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    const float* as = As + (kt % SK_STAGES) * SK_BM * SK_PITCH;
+    const float* ws = Ws + (kt % SK_STAGES) * SK_BN * SK_PITCH;
+#pragma unroll
+    for (int k4 = 0; k4 < SK_BK / 4; ++k4) {
+      float4 a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4*>(as + (ty * 4 + i) * SK_PITCH + k4 * 4);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = *reinterpret_cast<const float4*>(ws + (tx + 16 * j) * SK_PITCH + k4 * 4);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc[i][j] = fmaf(a[i].x, b[j].x, acc[i][j]);
+          acc[i][j] = fmaf(a[i].y, b[j].y, acc[i][j]);
+          acc[i][j] = fmaf(a[i].z, b[j].z, acc[i][j]);
+          acc[i][j] = fmaf(a[i].w, b[j].w, acc[i][j]);
+        }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    long long m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int n = n0 + tx + 16 * j;
+      ep.out[(size_t)m * ep.ldo + n] = apply_epilogue<MODE>(ep, acc[i][j], m, n);
     }
   }
 }

@@ -8,8 +8,10 @@
 //   * warp 1: single-thread tcgen05.mma.cta_group::1.kind::tf32 issuer, A and B from shared memory
 //     through UMMA descriptors, accumulators in TMEM (2 x 192 columns, double buffered so the
 //     epilogue of tile i overlaps the MMAs of tile i+1)
-//   * warp 2: TMEM allocator;  warps 4-7: epilogue (tcgen05.ld 32x32b -> registers -> fused
-//     bias / GELU / gate*y+residual -> 128-bit global stores)
+//   * warp 2: TMEM allocator;  warps 4-11: epilogue. Each warp owns a TMEM lane quarter and half
+//     of the tile's columns: tcgen05.ld 32x32b (thread = row) -> per-warp shared-memory transpose
+//     -> fused bias / GELU / gate*y+residual on *row-contiguous* float4s -> fully coalesced
+//     128-bit global loads/stores (4 x 128-byte lines per warp instruction)
 // Operands are fp32 bit patterns already rounded to TF32 (round-to-nearest) by their producers
 // (weights at pack time, activations by the LN / attention / GELU epilogues), so the tensor core's
 // truncation of the low 13 mantissa bits is exact.
@@ -28,11 +30,15 @@ namespace mdgen {
 constexpr int TC_BM = 128;
 constexpr int TC_BN = 192;
 constexpr int TC_BK = 32;                       // fp32 elements per K-block (128 bytes)
-constexpr int TC_STAGES = 5;
+constexpr int TC_STAGES = 4;
+constexpr int TC_THREADS = 384;                 // 4 control warps + 8 epilogue warps
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_EPI_PITCH = 36;                // floats per staged row (144 B: conflict-free float4)
+constexpr int TC_EPI_BYTES = TC_EPI_WARPS * 32 * TC_EPI_PITCH * 4;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
 constexpr int TC_B_BYTES = TC_BN * TC_BK * 4;   // 24 KB
 constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
-constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + TC_EPI_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int TC_TMEM_COLS = 512;               // 2 accumulator buffers x 192 columns (pow2 alloc)
 
 // ---- PTX wrappers ----------------------------------------------------------------------------
@@ -114,6 +120,24 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// erf-GELU with erf from Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7): two MUFU ops + ~10 FMA
+// instead of erff()'s branchy ~25 instructions (the fc1 epilogue is instruction-issue bound).
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * z * 1.4426950408889634f));
+  const float erf_abs = fmaf(-poly, e, 1.0f);
+  const float erf_v = copysignf(erf_abs, x);
+  return 0.5f * x * (1.0f + erf_v);
+}
+
 // ---- vectorised epilogue on 4 consecutive columns ------------------------------------------------
 template <int MODE>
 __device__ __forceinline__ void tc_epilogue4(const Epilogue& ep, const float* gate_row, long long m, int n,
@@ -123,7 +147,7 @@ __device__ __forceinline__ void tc_epilogue4(const Epilogue& ep, const float* ga
     float4 b = *reinterpret_cast<const float4*>(ep.bias + n);
     v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
   }
-  if (MODE == EPI_GELU) { v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w); }
+  if (MODE == EPI_GELU) { v.x = gelu_fast(v.x); v.y = gelu_fast(v.y); v.z = gelu_fast(v.z); v.w = gelu_fast(v.w); }
   if (MODE == EPI_RESID_GATE) {
     float4 g = *reinterpret_cast<const float4*>(gate_row + n);
     float4 r = *reinterpret_cast<const float4*>(ep.resid + (size_t)m * ep.ldo + n);
@@ -133,12 +157,12 @@ __device__ __forceinline__ void tc_epilogue4(const Epilogue& ep, const float* ga
     float4 r = *reinterpret_cast<const float4*>(ep.resid + (size_t)m * ep.ldo + n);
     v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
   }
-  if (ep.round_out) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
+  if (ep.round_out) { v.x = round_tf32_fast(v.x); v.y = round_tf32_fast(v.y); v.z = round_tf32_fast(v.z); v.w = round_tf32_fast(v.w); }
   *reinterpret_cast<float4*>(ep.out + (size_t)m * ep.ldo + n) = v;
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                          const __grid_constant__ CUtensorMap tmB, long long M,
                                                          int N, int K, Epilogue ep) {
   extern __shared__ uint8_t smem_raw[];
@@ -164,7 +188,7 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), TC_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -226,30 +250,43 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue warps (TMEM -> registers -> global) =====================
+    // ===================== epilogue warps (TMEM -> regs -> smem transpose -> global) =====================
     const int q = warp & 3;                                 // TMEM lane quarter of this warp
-    const int row_in_tile = q * 32 + lane;
+    const int half = (warp - 4) >> 2;                       // which 96-column half of the tile
+    float* stg = reinterpret_cast<float*>(sgen + TC_STAGES * TC_STAGE_BYTES + 256) + (warp - 4) * 32 * TC_EPI_PITCH;
+    const int rr0 = lane >> 3, c4 = lane & 7;
     uint32_t it = 0;
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
       const uint32_t buf = it & 1u, bphase = (it >> 1) & 1u;
-      const long long m = (tile / n_blocks) * TC_BM + row_in_tile;
-      const int n0 = (int)(tile % n_blocks) * TC_BN;
+      const long long mbase = (tile / n_blocks) * TC_BM + q * 32;
+      const int n0 = (int)(tile % n_blocks) * TC_BN + half * (TC_BN / 2);
       mbar_wait(tfull_bar(buf), bphase);
       tc_fence_after();
-      const float* gate_row = nullptr;
-      if (MODE == EPI_RESID_GATE && m < M) gate_row = mod_row(ep.mod, m) + ep.gate_off;
 #pragma unroll 1
-      for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+      for (int c0 = 0; c0 < TC_BN / 2; c0 += 32) {
         uint32_t v[32];
-        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * TC_BN + c0, v);
+        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * TC_BN + half * (TC_BN / 2) + c0, v);
         tc_ld_wait();
-        if (m < M) {
+        // thread = row: write the 32 columns of this row into the warp's staging tile
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            tc_epilogue4<MODE>(ep, gate_row, m, n0 + c0 + 4 * j, __uint_as_float(v[4 * j]),
-                               __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
-                               __uint_as_float(v[4 * j + 3]));
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(stg + lane * TC_EPI_PITCH + 4 * j) =
+              make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                          __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+        __syncwarp();
+        // 8 lanes cover one 128-byte row segment; a warp instruction covers 4 rows
+#pragma unroll
+        for (int itr = 0; itr < 8; ++itr) {
+          const int rr = itr * 4 + rr0;
+          const long long m = mbase + rr;
+          const float4 a = *reinterpret_cast<const float4*>(stg + rr * TC_EPI_PITCH + 4 * c4);
+          if (m < M) {
+            const float* gate_row = nullptr;
+            if (MODE == EPI_RESID_GATE) gate_row = mod_row(ep.mod, m) + ep.gate_off;
+            tc_epilogue4<MODE>(ep, gate_row, m, n0 + c0 + 4 * c4, a.x, a.y, a.z, a.w);
+          }
         }
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
@@ -338,7 +375,7 @@ inline int tc_launch_mode(const CUtensorMap& ta, const CUtensorMap& tb, long lon
     }
     configured = true;
   }
-  gemm_tc_kernel<MODE><<<grid, 256, TC_SMEM_BYTES, s>>>(ta, tb, M, N, K, ep);
+  gemm_tc_kernel<MODE><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(ta, tb, M, N, K, ep);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     if (err) *err = std::string("gemm_tc launch: ") + cudaGetErrorString(e);

@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(128) ipa_attn_kernel(
   float lz = R[2] * dx + R[5] * dy + R[8] * dz;
   float nrm = sqrtf(lx * lx + ly * ly + lz * lz + 1e-8f);
   float* co = cat + (size_t)row * kIpaCat;
-  auto rnd = [&](float v) { return round_out ? round_tf32(v) : v; };
+  auto rnd = [&](float v) { return round_out ? round_tf32_fast(v) : v; };
   co[h * 32 + lane] = rnd(o);
   if (lane < 8) {
     co[128 + h * 8 + lane] = rnd(lx);

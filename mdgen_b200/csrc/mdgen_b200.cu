@@ -39,7 +39,7 @@ struct MhaW {
   float *wqkv_tc, *wo_tc;
 };
 struct IpaLayerW {
-  float *ln_g, *ln_b, *head_w, *wproj, *bproj, *wout, *bout;
+  float *ln_g, *ln_b, *head_w, *wproj, *bproj, *wout, *bout, *wproj_tc, *wout_tc;
   MhaW mha;
   float *w1, *b1, *w2, *b2, *w1_tc, *w2_tc;
 };
@@ -68,7 +68,7 @@ struct mdgen_handle {
   int use_tc = 1;      // tcgen05 TF32 GEMMs for the token GEMMs (0 = fp32 SIMT validation path)
 #endif
   int use_tc_attn = 1; // tcgen05 attention for sequences longer than 64 (needs use_tc)
-  int tc_min_rows = 1024;  // below this many rows the SIMT GEMM is used (latency-bound shapes)
+  int tc_min_rows = 1024;   // fewer rows (the IPA key-frame trunk) stay on the exact-fp32 skinny GEMM  // below this many rows the SIMT GEMM is used (latency-bound shapes)
   int profile = 0;
   std::vector<ProfEntry> prof;
 
@@ -97,6 +97,8 @@ struct mdgen_handle {
         *hidi = nullptr, *frot = nullptr, *ftrans = nullptr, *fmask = nullptr, *ipa_out = nullptr;
   float *tvals = nullptr, *sinus = nullptr, *h1 = nullptr, *st = nullptr, *mod = nullptr, *dt = nullptr;
   float *xbuf = nullptr, *xbuf2 = nullptr;  // ping-pong Euler state [N, D<=28]
+  uint8_t* attn_scratch = nullptr;           // UMMA-ready key-tile images of the tcgen05 attention
+  size_t attn_scratch_bytes = 0;
   int* step = nullptr;
 };
 
@@ -305,6 +307,18 @@ int gemm(mdgen_handle* h, cudaStream_t s, int mode, const float* A, int lda, con
     return MDGEN_OK;
   }
 #endif
+  if (M <= 4096 && N % SK_BN == 0 && K % SK_BK == 0 && lda % 4 == 0 && ldw % 4 == 0) {
+    dim3 g((unsigned)((M + SK_BM - 1) / SK_BM), (unsigned)(N / SK_BN));
+    switch (mode) {
+      case EPI_STORE: gemm_skinny_kernel<EPI_STORE><<<g, 128, SK_SMEM_BYTES, s>>>(A, lda, W, ldw, M, N, K, ep); break;
+      case EPI_GELU: gemm_skinny_kernel<EPI_GELU><<<g, 128, SK_SMEM_BYTES, s>>>(A, lda, W, ldw, M, N, K, ep); break;
+      case EPI_RESID_GATE: gemm_skinny_kernel<EPI_RESID_GATE><<<g, 128, SK_SMEM_BYTES, s>>>(A, lda, W, ldw, M, N, K, ep); break;
+      case EPI_RESID: gemm_skinny_kernel<EPI_RESID><<<g, 128, SK_SMEM_BYTES, s>>>(A, lda, W, ldw, M, N, K, ep); break;
+      default: h->err = "bad epilogue mode"; return MDGEN_E_INVALID;
+    }
+    CHECK_LAUNCH(h);
+    return MDGEN_OK;
+  }
   dim3 grid((unsigned)((M + SG_BM - 1) / SG_BM), (unsigned)((N + SG_BN - 1) / SG_BN));
   switch (mode) {
     case EPI_STORE: gemm_simt_kernel<EPI_STORE><<<grid, 256, 0, s>>>(A, lda, W, ldw, M, N, K, ep); break;
@@ -337,7 +351,15 @@ int attention(mdgen_handle* h, cudaStream_t s, const float* qkv, const float* ma
   p.cosT = h->cosT; p.sinT = h->sinT; p.out = out; p.round_out = round_out; p.sm = sm;
 #ifndef MDGEN_NO_TC
   if (h->use_tc && h->use_tc_attn && sm.S > 64) {
-    if (attn_tc_launch(p, s, &h->err)) return MDGEN_E_CUDA;
+    size_t need = attn_tc_scratch_bytes(sm);
+    if (need > h->attn_scratch_bytes) {
+      if (h->attn_scratch) dev_free(h, h->attn_scratch);
+      h->attn_scratch = nullptr; h->attn_scratch_bytes = 0;
+      TRY(dev_alloc(h, reinterpret_cast<void**>(&h->attn_scratch), need));
+      CUDA_TRY(h, cudaMemsetAsync(h->attn_scratch, 0, need, s));   // V^T pad rows must read as zeros
+      h->attn_scratch_bytes = need;
+    }
+    if (attn_tc_launch(p, h->attn_scratch, s, &h->err)) return MDGEN_E_CUDA;
     h->launches++;
     return MDGEN_OK;
   }
@@ -412,7 +434,8 @@ int run_step(mdgen_handle* h, cudaStream_t s, const mdgen_cond* c, const float* 
   const long long N = (long long)B * T * L;
   const bool two = !h->cfg.sim_condition && (h->cfg.tps_condition || h->cfg.inpainting);
   const long long BL = (long long)B * L, rows = (two ? 2 : 1) * BL;
-  const int rt = h->use_tc ? 1 : 0;  // round GEMM-operand activations to TF32
+  const int rt = (h->use_tc && N >= h->tc_min_rows) ? 1 : 0;  // round GEMM-operand activations to TF32
+  const int rti = (h->use_tc && rows >= h->tc_min_rows) ? 1 : 0;   // same, IPA-trunk GEMMs
 
   ModRef modi{h->mod, step_ptr, h->modw, bstride, L, B};
   ModRef modm{h->mod, step_ptr, h->modw, bstride, T * L, B};
@@ -430,28 +453,32 @@ int run_step(mdgen_handle* h, cudaStream_t s, const mdgen_cond* c, const float* 
     for (int i = 0; i < n; ++i) {
       const IpaLayerW& w = h->ipa[i];
       int off = i * 6 * kC;
-      ln_affine_kernel<false><<<(unsigned)((rows * 32 + 255) / 256), 256, 0, s>>>(h->xi, h->xni, w.ln_g,
-                                                                                w.ln_b, rows);
+      if (rti)
+        ln_affine_kernel<true><<<(unsigned)((rows * 32 + 255) / 256), 256, 0, s>>>(h->xi, h->xni, w.ln_g, w.ln_b, rows);
+      else
+        ln_affine_kernel<false><<<(unsigned)((rows * 32 + 255) / 256), 256, 0, s>>>(h->xi, h->xni, w.ln_g, w.ln_b, rows);
       CHECK_LAUNCH(h);
-      TRY(gemm(h, s, EPI_STORE, h->xni, kC, w.wproj, nullptr, kC, rows, kIpaProj, kC,
+      TRY(gemm(h, s, EPI_STORE, h->xni, kC, w.wproj, w.wproj_tc, kC, rows, kIpaProj, kC,
                make_epi(w.bproj, h->proj, kIpaProj), "ipa_gemm"));
       ipa_points_kernel<<<(unsigned)((rows * 96 + 255) / 256), 256, 0, s>>>(h->proj, h->frot, h->ftrans, rows);
       CHECK_LAUNCH(h);
       ipa_attn_kernel<<<(unsigned)rows, 128, 4 * L * sizeof(float), s>>>(h->proj, h->frot, h->ftrans, h->fmask,
-                                                                         w.head_w, h->cat, L, 0);
+                                                                         w.head_w, h->cat, L, rti);
       CHECK_LAUNCH(h);
       Epilogue eo = make_epi(w.bout, h->xi, kC);
       eo.resid = h->xi;
-      TRY(gemm(h, s, EPI_RESID, h->cat, kIpaCat, w.wout, nullptr, kIpaCat, rows, kC, kIpaCat, eo, "ipa_gemm"));
-      TRY(ln_mod<false>(h, s, h->xi, h->xni, modi, off + 0, off + kC, rows));
-      TRY(gemm(h, s, EPI_STORE, h->xni, kC, w.mha.wqkv, nullptr, kC, rows, kQKV, kC,
+      TRY(gemm(h, s, EPI_RESID, h->cat, kIpaCat, w.wout, w.wout_tc, kIpaCat, rows, kC, kIpaCat, eo, "ipa_gemm"));
+      if (rti) TRY(ln_mod<true>(h, s, h->xi, h->xni, modi, off + 0, off + kC, rows));
+      else TRY(ln_mod<false>(h, s, h->xi, h->xni, modi, off + 0, off + kC, rows));
+      TRY(gemm(h, s, EPI_STORE, h->xni, kC, w.mha.wqkv, w.mha.wqkv_tc, kC, rows, kQKV, kC,
                make_epi(w.mha.bqkv, h->qkvi, kQKV), "ipa_gemm"));
-      TRY(attention(h, s, h->qkvi, h->fmask, w.mha, h->atti, smi, 0, "ipa_mha"));
-      TRY(gemm(h, s, EPI_RESID_GATE, h->atti, kC, w.mha.wo, nullptr, kC, rows, kC, kC,
+      TRY(attention(h, s, h->qkvi, h->fmask, w.mha, h->atti, smi, rti, "ipa_mha"));
+      TRY(gemm(h, s, EPI_RESID_GATE, h->atti, kC, w.mha.wo, w.mha.wo_tc, kC, rows, kC, kC,
                make_epi_gate(w.mha.bo, h->xi, kC, modi, off + 2 * kC), "ipa_gemm"));
-      TRY(ln_mod<false>(h, s, h->xi, h->xni, modi, off + 3 * kC, off + 4 * kC, rows));
-      TRY(gemm(h, s, EPI_GELU, h->xni, kC, w.w1, nullptr, kC, rows, kFF, kC, make_epi(w.b1, h->hidi, kFF), "ipa_gemm"));
-      TRY(gemm(h, s, EPI_RESID_GATE, h->hidi, kFF, w.w2, nullptr, kFF, rows, kC, kFF,
+      if (rti) TRY(ln_mod<true>(h, s, h->xi, h->xni, modi, off + 3 * kC, off + 4 * kC, rows));
+      else TRY(ln_mod<false>(h, s, h->xi, h->xni, modi, off + 3 * kC, off + 4 * kC, rows));
+      TRY(gemm(h, s, EPI_GELU, h->xni, kC, w.w1, w.w1_tc, kC, rows, kFF, kC, make_epi(w.b1, h->hidi, kFF, rti), "ipa_gemm"));
+      TRY(gemm(h, s, EPI_RESID_GATE, h->hidi, kFF, w.w2, w.w2_tc, kFF, rows, kC, kFF,
                make_epi_gate(w.b2, h->xi, kC, modi, off + 5 * kC), "ipa_gemm"));
     }
     long long ne = BL * kC;
@@ -618,6 +645,8 @@ int mdgen_finalize_weights(mdgen_handle* h, void* stream) {
     TRY(pack_new(h, s, p + "ipa.head_weights", 1, kIpaH, &w.head_w));
     TRY(dev_alloc_t(h, &w.wproj, (size_t)kIpaProj * kC));
     TRY(dev_alloc_t(h, &w.bproj, (size_t)kIpaProj));
+    CUDA_TRY(h, cudaMemsetAsync(w.wproj, 0, (size_t)kIpaProj * kC * sizeof(float), s));   // rows 672..767 = pad
+    CUDA_TRY(h, cudaMemsetAsync(w.bproj, 0, (size_t)kIpaProj * sizeof(float), s));
     TRY(pack(h, s, p + "ipa.linear_q.weight", 128, kC, w.wproj, kC, 0, 1.f, 0));
     TRY(pack(h, s, p + "ipa.linear_kv.weight", 256, kC, w.wproj, kC, 128, 1.f, 0));
     TRY(pack(h, s, p + "ipa.linear_q_points.weight", 96, kC, w.wproj, kC, 384, 1.f, 0));
@@ -626,7 +655,9 @@ int mdgen_finalize_weights(mdgen_handle* h, void* stream) {
     TRY(pack(h, s, p + "ipa.linear_kv.bias", 1, 256, w.bproj + 128, kIpaProj, 0, 1.f, 0));
     TRY(pack(h, s, p + "ipa.linear_q_points.bias", 1, 96, w.bproj + 384, kIpaProj, 0, 1.f, 0));
     TRY(pack(h, s, p + "ipa.linear_kv_points.bias", 1, 192, w.bproj + 480, kIpaProj, 0, 1.f, 0));
+    TRY(tc_copy(h, s, w.wproj, (size_t)kIpaProj * kC, &w.wproj_tc));
     TRY(pack_new(h, s, p + "ipa.linear_out.weight", kC, kIpaCat, &w.wout));
+    TRY(tc_copy(h, s, w.wout, (size_t)kC * kIpaCat, &w.wout_tc));
     TRY(pack_new(h, s, p + "ipa.linear_out.bias", 1, kC, &w.bout));
     TRY(pack_mha(h, s, p + "mha_l.", &w.mha));
     TRY(pack_new(h, s, p + "fc1.weight", kFF, kC, &w.w1));
