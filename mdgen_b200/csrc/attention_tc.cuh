@@ -2,24 +2,30 @@
 // softmax(Q K^T + key-padding) V with bias-KV token and RoPE, scores never leave the SM
 // (restates mdgen/model/mha.py:260-397; K8-K13 of SURVEY.md §2c collapse into this kernel).
 //
-// One CTA = one (sequence, head); 256 threads, two CTAs per SM (the second CTA's softmax fills the
-// tensor-pipe / barrier bubbles of the first):
-//   warps 0-3  "softmax" : thread r owns query row r of the current 128-query tile == TMEM lane r.
-//                          Stages the RoPE'd, TF32-rounded Q tile, reads S from TMEM, exact online
-//                          softmax (fp32), writes P back over S in TMEM, accumulates O in registers.
-//                          Thread 0 is also the single MMA-issuing thread.
-//   prologue (all warps) : builds, once per (sequence, head), the UMMA-ready images of every key tile
-//                          (K rotated by RoPE, V transposed, both TF32-rounded, K-major SWIZZLE_128B,
-//                          plus the additive key mask) in an L2-resident global scratch.
+// One CTA = one (sequence, head, 128-query tile); 160 threads, three CTAs per SM (128 TMEM columns and ~70 KB of
+// shared memory each), so three independent softmax warps per SM sub-partition hide each other's
+// TMEM / mbarrier latencies:
+//   (attn_prep_kernel)   : pre-pass that builds, once per (sequence, head), the UMMA-ready images of
+//                          every 96-key tile (K rotated by RoPE, V transposed, TF32-rounded,
+//                          K-major SWIZZLE_128B, plus additive key mask and |k| bound) in a global
+//                          scratch; the CTAs of all query tiles of that (sequence, head) are adjacent
+//                          in the grid, so they share those images through L2.
 //   warp 4 lane 0        : producer - one cp.async.bulk (TMA 1-D) per key tile refills a 2-stage
-//                          shared-memory ring from that scratch for each of the query tiles.
-// Per key tile:  S[128x128] = Q·K^T   (3 x tcgen05.mma kind::tf32, K = 24 = 3 x 8, A/B from smem)
+//                          shared-memory ring from that scratch, for every query tile.
+//   warps 0-3  "softmax" : thread r owns query row r of the current 128-query tile == TMEM lane r.
+//                          Stages the RoPE'd Q tile, reads S from TMEM, fp32 online softmax, writes P
+//                          back over S in TMEM, accumulates O in registers. Thread 0 issues the MMAs.
+// Per key tile:  S[128x96] = Q·K^T    (3 x tcgen05.mma kind::tf32, K = 24 = 3 x 8, A/B from smem)
 //                P = exp2(S - m)      (softmax warps, TMEM -> regs -> TMEM, in place)
-//                O_t[128x32] = P·V    (16 x tcgen05.mma kind::tf32, A = P from TMEM, B = V^T smem)
-//                acc = acc*alpha + O_t (registers; no TMEM rescale pass needed)
+//                O_t[128x32] = P·V    (12 x tcgen05.mma kind::tf32, A = P from TMEM, B = V^T smem)
+//                acc = acc*alpha + O_t (registers; no TMEM rescale pass)
+// Online softmax reference: the exact two-pass (row max, then exp) is used for a tile only when the
+// row has no reference yet or when the Cauchy-Schwarz bound |q_i|*max_j|k_j| could exceed the
+// reference by 2^100; otherwise the tile is exponentiated in a single TMEM pass against the
+// existing reference (no overflow is possible, and softmax is shift invariant).
 // head_dim 24 is padded to 32 only in shared-memory row pitch (128-byte rows); the QK^T MMAs read
-// just the three valid 32-byte K-chunks. The softmax (MUFU ex2) is the roofline of this kernel,
-// not the tensor pipe: 96 MMA flops per score element vs. one exp.
+// just the three valid 32-byte K-chunks. MUFU ex2 is the roofline of this kernel, not the tensor
+// pipe: 96 MMA flops per score element vs. one exp.
 #pragma once
 #include "attention_simt.cuh"
 #include "gemm_tc.cuh"
@@ -27,14 +33,16 @@
 namespace mdgen {
 
 constexpr int AT_QT = 128;                      // queries per tile (UMMA M)
-constexpr int AT_KT = 128;                      // keys per tile (UMMA N of QK^T, K of PV)
-constexpr int AT_TILE_BYTES = 128 * 128;        // 128 rows x 128-byte pitch
-constexpr int AT_VT_BYTES = 4 * 4096;           // V^T: 4 k-atoms of [32 d-rows x 32 keys]
-constexpr int AT_KM_BYTES = 512 + 16;            // additive key mask (128 floats) + "tile has masked keys" flag
-constexpr int AT_IMG_BYTES = AT_TILE_BYTES + AT_VT_BYTES + AT_KM_BYTES;   // one staged key tile: K | V^T | mask
-constexpr int AT_STAGE_BYTES = 34 * 1024;       // smem stage pitch (keeps K / V^T 1024-byte aligned)
-constexpr int AT_SMEM_BYTES = 1024 /*align*/ + AT_TILE_BYTES /*Q*/ + 2 * AT_STAGE_BYTES + 128;
-constexpr int AT_TMEM_COLS = 256;               // S/P: cols [0,128), O tile: cols [128,160)
+constexpr int AT_KT = 96;                       // keys per tile (UMMA N of QK^T, K of PV)
+constexpr int AT_THREADS = 160;
+constexpr int AT_Q_BYTES = 128 * 128;           // Q tile: 128 rows x 128-byte pitch
+constexpr int AT_K_BYTES = AT_KT * 128;         // K tile
+constexpr int AT_VT_BYTES = (AT_KT / 32) * 4096;   // V^T: k-atoms of [32 d-rows x 32 keys]
+constexpr int AT_KM_FLOATS = 128 + 4 + 4;       // key mask | per-slice "has masked key" flags | per-slice max |k|
+constexpr int AT_IMG_BYTES = AT_K_BYTES + AT_VT_BYTES + AT_KM_FLOATS * 4;   // one staged key tile
+constexpr int AT_STAGE_BYTES = 26 * 1024;       // smem stage pitch (keeps K / V^T 1024-byte aligned)
+constexpr int AT_SMEM_BYTES = 1024 /*align*/ + AT_Q_BYTES + 2 * AT_STAGE_BYTES + 128;
+constexpr int AT_TMEM_COLS = 128;               // S/P: cols [0,96), O tile: cols [96,128)
 
 __device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&v)[32]) {
   asm volatile(
@@ -113,44 +121,26 @@ __device__ __forceinline__ uint32_t sw128_off(int r, int c) {
   return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
 }
 
-__global__ void __launch_bounds__(256, 2) attn_tc_kernel(AttnParams p, uint8_t* __restrict__ scratch) {
-  extern __shared__ uint8_t smem_raw[];
+// Pre-pass: builds, once per (sequence, head), the UMMA-ready images of every 96-key tile in a
+// global scratch: K rotated by RoPE, V transposed, TF32-rounded, K-major SWIZZLE_128B layout, plus
+// the additive key mask, per-slice "has masked key" flags and per-slice max |k| (overflow bound).
+// The attention CTAs of all query tiles of that (sequence, head) then refill their shared-memory
+// ring from these images with plain 1-D TMA bulk copies (L2 hits: they run concurrently).
+__global__ void __launch_bounds__(256) attn_prep_kernel(AttnParams p, uint8_t* __restrict__ scratch) {
   const SeqMap& sm = p.sm;
-  const uint32_t raw = smem_u32(smem_raw);
-  const uint32_t sbase = (raw + 1023u) & ~1023u;
-  uint8_t* sgen = smem_raw + (sbase - raw);
-  // carve-up
-  const uint32_t q_off = 0;
-  const uint32_t st_off = AT_TILE_BYTES;                       // stage s: [K 16K | V^T 16K | kmask+flag]
-  const uint32_t bar_off = AT_TILE_BYTES + 2 * AT_STAGE_BYTES;
-  const uint32_t b_sfull = sbase + bar_off, b_ofull = b_sfull + 8;
-  auto b_kvfull = [&](int s) { return sbase + bar_off + 16 + 8 * s; };
-  auto b_kvfree = [&](int s) { return sbase + bar_off + 32 + 8 * s; };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sgen + bar_off + 48);
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
   const int h = blockIdx.x % kH;
   const long long s = blockIdx.x / kH;
   const int S = sm.S, nkeys = S + 1;
-  const int nqt = (S + AT_QT - 1) / AT_QT, nkt = (nkeys + AT_KT - 1) / AT_KT;
-  uint8_t* img = scratch + (size_t)blockIdx.x * nkt * AT_IMG_BYTES;   // this CTA's key-tile images
-
-  if (tid == 0) {
-    mbar_init(b_sfull, 1); mbar_init(b_ofull, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(b_kvfull(i), 1); mbar_init(b_kvfree(i), 1); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                 ::"r"(smem_u32((const void*)tmem_slot)), "r"((uint32_t)AT_TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
+  const int nkt = (nkeys + AT_KT - 1) / AT_KT;
+  uint8_t* img = scratch + (size_t)blockIdx.x * nkt * AT_IMG_BYTES;
   // =============================== prologue: key-tile images ===============================
-  // (rows 24..31 of every V^T atom are never written: the scratch is zero-filled at allocation)
+  // (rows 24..31 of every V^T atom are never written: the scratch is zero-filled at allocation;
+  //  stale finite data there only reaches the unused accumulator columns 24..31)
   for (int j = tid; j < nkt * AT_KT; j += 256) {
-    const int kt = j >> 7, r = j & 127;
+    const int kt = j / AT_KT, r = j - kt * AT_KT;
     uint8_t* kbase = img + (size_t)kt * AT_IMG_BYTES;
-    uint8_t* vbase = kbase + AT_TILE_BYTES;
+    uint8_t* vbase = kbase + AT_K_BYTES;
     float* kmask = reinterpret_cast<float*>(vbase + AT_VT_BYTES);
     float k[kHD], v[kHD];
     float mval = 0.f;
@@ -173,11 +163,12 @@ __global__ void __launch_bounds__(256, 2) attn_tc_kernel(AttnParams p, uint8_t* 
       mval = -INFINITY;
     }
     if (j <= S) rope24(k, p.cosT + j * kHalf, p.sinT + j * kHalf);
+    float kn2 = 0.f;
 #pragma unroll
-    for (int c = 0; c < 6; ++c) {
-      float4 o = make_float4(round_tf32_fast(k[4*c]), round_tf32_fast(k[4*c+1]), round_tf32_fast(k[4*c+2]), round_tf32_fast(k[4*c+3]));
-      *reinterpret_cast<float4*>(kbase + sw128_off(r, c)) = o;
-    }
+    for (int i = 0; i < kHD; ++i) { k[i] = round_tf32(k[i]); kn2 = fmaf(k[i], k[i], kn2); }
+#pragma unroll
+    for (int c = 0; c < 6; ++c)
+      *reinterpret_cast<float4*>(kbase + sw128_off(r, c)) = make_float4(k[4*c], k[4*c+1], k[4*c+2], k[4*c+3]);
     {
       uint8_t* ab = vbase + (r >> 5) * 4096;
       const int kc = (r & 31) >> 2, kw = r & 3;
@@ -186,22 +177,60 @@ __global__ void __launch_bounds__(256, 2) attn_tc_kernel(AttnParams p, uint8_t* 
         reinterpret_cast<float*>(ab + sw128_off(d, kc))[kw] = round_tf32_fast(v[d]);
     }
     kmask[r] = mval;
-    // per-slice flag (ints 128..131 of the mask block): any masked / out-of-range key among the
-    // 32 keys this warp just wrote
+    // per 32-key slice: "has a masked / out-of-range key" flag and max |k| (for the overflow bound)
     const unsigned any = __ballot_sync(0xffffffffu, mval != 0.f);
-    if (lane == 0) reinterpret_cast<int*>(kmask + 128)[r >> 5] = any ? 1 : 0;
+    const float kn = warp_max(sqrtf(kn2));
+    if (lane == 0) {
+      reinterpret_cast<int*>(kmask + 128)[r >> 5] = any ? 1 : 0;
+      kmask[132 + (r >> 5)] = kn;
+    }
   }
-  asm volatile("fence.proxy.async;" ::: "memory");             // generic global writes -> async-proxy (bulk copy) reads
+}
+
+__global__ void __launch_bounds__(AT_THREADS, 3) attn_tc_kernel(AttnParams p, uint8_t* __restrict__ scratch) {
+  extern __shared__ uint8_t smem_raw[];
+  const SeqMap& sm = p.sm;
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t sbase = (raw + 1023u) & ~1023u;
+  uint8_t* sgen = smem_raw + (sbase - raw);
+  // carve-up
+  const uint32_t q_off = 0;
+  const uint32_t st_off = AT_Q_BYTES;                          // stage s: [K | V^T | mask block]
+  const uint32_t bar_off = AT_Q_BYTES + 2 * AT_STAGE_BYTES;
+  const uint32_t b_sfull = sbase + bar_off, b_ofull = b_sfull + 8;
+  auto b_kvfull = [&](int s) { return sbase + bar_off + 16 + 8 * s; };
+  auto b_kvfree = [&](int s) { return sbase + bar_off + 32 + 8 * s; };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sgen + bar_off + 48);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int S = sm.S, nkeys = S + 1;
+  const int nqt = (S + AT_QT - 1) / AT_QT, nkt = (nkeys + AT_KT - 1) / AT_KT;
+  const int qt0 = blockIdx.x % nqt;                     // query tile of this CTA (fastest: the CTAs
+  const long long sh = blockIdx.x / nqt;                // sharing one set of key images run together)
+  const int h = (int)(sh % kH);
+  const long long s = sh / kH;
+  const uint8_t* img = scratch + (size_t)sh * nkt * AT_IMG_BYTES;
+
+  if (tid == 0) {
+    mbar_init(b_sfull, 1); mbar_init(b_ofull, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(b_kvfull(i), 1); mbar_init(b_kvfree(i), 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32((const void*)tmem_slot)), "r"((uint32_t)AT_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
+  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + AT_KT;
 
   if (warp == 4) {
     if (lane == 0) {
       // =============================== producer (TMA 1-D bulk copies) ===============================
-      for (int qt = 0, g = 0; qt < nqt; ++qt) {
+      for (int qt = qt0, g = 0; qt < qt0 + 1; ++qt) {
         for (int kt = 0; kt < nkt; ++kt, ++g) {
           const int st = g & 1, use = g >> 1;
           mbar_wait_backoff(b_kvfree(st), (uint32_t)((use & 1) ^ 1));   // PV of the previous user retired
@@ -215,7 +244,7 @@ __global__ void __launch_bounds__(256, 2) attn_tc_kernel(AttnParams p, uint8_t* 
         }
       }
     }
-  } else if (warp < 4) {
+  } else {
     // =============================== softmax + MMA issue ===============================
     const int r = tid;                              // query row in tile == TMEM lane
     const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
@@ -223,11 +252,12 @@ __global__ void __launch_bounds__(256, 2) attn_tc_kernel(AttnParams p, uint8_t* 
     constexpr uint32_t idesc_pv = umma_idesc_tf32(AT_QT, 32);
     const float LOG2E = 1.4426950408889634f;
     uint32_t ph_s = 0, ph_o = 0;
-    for (int qt = 0, g = 0; qt < nqt; ++qt) {
+    for (int qt = qt0, g = 0; qt < qt0 + 1; ++qt) {
       // ---- stage the Q tile (all earlier MMAs reading it have completed: last o_full was waited)
       const int e = qt * AT_QT + r;
       const bool qok = e < S;
       const long long tq = seq_token(sm, s, qok ? e : S - 1);
+      float qnorm;
       {
         float q[kHD];
         const float4* qp = reinterpret_cast<const float4*>(p.qkv + (size_t)tq * kQKV + h * kHD);
@@ -235,12 +265,13 @@ __global__ void __launch_bounds__(256, 2) attn_tc_kernel(AttnParams p, uint8_t* 
         for (int i = 0; i < 6; ++i) { float4 a = qp[i]; q[4*i] = a.x; q[4*i+1] = a.y; q[4*i+2] = a.z; q[4*i+3] = a.w; }
         const int pe = qok ? e : S - 1;
         rope24(q, p.cosT + pe * kHalf, p.sinT + pe * kHalf);
+        float qn2 = 0.f;
 #pragma unroll
-        for (int c = 0; c < 6; ++c) {
-          float4 o = make_float4(round_tf32_fast(q[4*c] * LOG2E), round_tf32_fast(q[4*c+1] * LOG2E),
-                                 round_tf32_fast(q[4*c+2] * LOG2E), round_tf32_fast(q[4*c+3] * LOG2E));
-          *reinterpret_cast<float4*>(sgen + q_off + sw128_off(r, c)) = o;
-        }
+        for (int i = 0; i < kHD; ++i) { q[i] = round_tf32(q[i] * LOG2E); qn2 = fmaf(q[i], q[i], qn2); }
+        qnorm = sqrtf(qn2) * 1.001f;
+#pragma unroll
+        for (int c = 0; c < 6; ++c)
+          *reinterpret_cast<float4*>(sgen + q_off + sw128_off(r, c)) = make_float4(q[4*c], q[4*c+1], q[4*c+2], q[4*c+3]);
       }
       fence_async_smem();
       named_bar_sync(2, 128);
@@ -266,20 +297,25 @@ __global__ void __launch_bounds__(256, 2) attn_tc_kernel(AttnParams p, uint8_t* 
         const int st = g & 1;
         mbar_wait(b_sfull, ph_s); ph_s ^= 1u;
         tc_fence_after();
-        const float* kmask = reinterpret_cast<const float*>(sgen + st_off + st * AT_STAGE_BYTES + AT_TILE_BYTES + AT_VT_BYTES);
-        const int4 fl = *reinterpret_cast<const int4*>(kmask + 128);   // one flag per 32-key slice
-        const bool masked = (fl.x | fl.y | fl.z | fl.w) != 0;
-        // ---- pass 1: exact row max of this tile (chunk c+1 is in flight while chunk c is reduced)
-        float tmax = -INFINITY;
-        {
+        const float* kmask = reinterpret_cast<const float*>(sgen + st_off + st * AT_STAGE_BYTES + AT_K_BYTES + AT_VT_BYTES);
+        const int4 fl = *reinterpret_cast<const int4*>(kmask + 128);      // one flag per 32-key slice
+        const bool masked = (fl.x | fl.y | fl.z) != 0;
+        const float4 kn = *reinterpret_cast<const float4*>(kmask + 132);  // max |k| per slice
+        const float bound = qnorm * fmaxf(kn.x, fmaxf(kn.y, kn.z));       // >= every score of this row & tile
+        // exact two-pass only when this row has no reference yet or the bound could overflow exp2
+        const bool need_exact = __any_sync(0xffffffffu, (m_run == -INFINITY) || (bound - m_run > 100.f));
+        float m_new = m_run;
+        if (need_exact) {
+          // ---- pass 1: exact row max of this tile (chunk c+1 in flight while chunk c is reduced)
+          float tmax = -INFINITY;
           uint32_t va[16], vb[16];
           tc_ld16(tmem_S + lane_addr, va);
           tc_ld_wait();
 #pragma unroll
-          for (int cc = 0; cc < 8; ++cc) {
+          for (int cc = 0; cc < AT_KT / 16; ++cc) {
             uint32_t (&cur)[16] = (cc & 1) ? vb : va;
             uint32_t (&nxt)[16] = (cc & 1) ? va : vb;
-            if (cc < 7) tc_ld16(tmem_S + lane_addr + (cc + 1) * 16, nxt);
+            if (cc < AT_KT / 16 - 1) tc_ld16(tmem_S + lane_addr + (cc + 1) * 16, nxt);
             if (masked) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) tmax = fmaxf(tmax, __uint_as_float(cur[i]) + kmask[cc * 16 + i]);
@@ -287,25 +323,25 @@ __global__ void __launch_bounds__(256, 2) attn_tc_kernel(AttnParams p, uint8_t* 
 #pragma unroll
               for (int i = 0; i < 16; ++i) tmax = fmaxf(tmax, __uint_as_float(cur[i]));
             }
-            if (cc < 7) tc_ld_wait();
+            if (cc < AT_KT / 16 - 1) tc_ld_wait();
           }
+          m_new = fmaxf(m_run, tmax);
         }
-        const float m_new = fmaxf(m_run, tmax);
         const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-        const float alpha = ex2f(m_run - m_use);
-        // ---- pass 2: P = exp2(S - m), written back over S. The denominator sums the exact fp32 p;
-        // the numerator operand is rounded to TF32 by adding half an ulp (the MMA truncates the low
-        // 13 mantissa bits), so its rounding error is zero-mean.
+        const float alpha = ex2f(m_run - m_use);      // 1 when the reference is unchanged
+        // ---- P = exp2(S - m), written back over S. The denominator sums the exact fp32 p; the
+        // numerator operand is rounded to TF32 by adding half an ulp (the MMA truncates the low 13
+        // mantissa bits), so its rounding error is zero-mean.
         float lsum = 0.f;
         {
           uint32_t va[16], vb[16];
           tc_ld16(tmem_S + lane_addr, va);
           tc_ld_wait();
 #pragma unroll
-          for (int cc = 0; cc < 8; ++cc) {
+          for (int cc = 0; cc < AT_KT / 16; ++cc) {
             uint32_t (&cur)[16] = (cc & 1) ? vb : va;
             uint32_t (&nxt)[16] = (cc & 1) ? va : vb;
-            if (cc < 7) tc_ld16(tmem_S + lane_addr + (cc + 1) * 16, nxt);
+            if (cc < AT_KT / 16 - 1) tc_ld16(tmem_S + lane_addr + (cc + 1) * 16, nxt);
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               float x = __uint_as_float(cur[i]);
@@ -314,7 +350,7 @@ __global__ void __launch_bounds__(256, 2) attn_tc_kernel(AttnParams p, uint8_t* 
               lsum += pv;
               cur[i] = __float_as_uint(pv) + 0x1000u;
             }
-            if (cc < 7) tc_ld_wait();
+            if (cc < AT_KT / 16 - 1) tc_ld_wait();
             tc_st16(tmem_S + lane_addr + cc * 16, cur);
           }
         }
@@ -325,7 +361,7 @@ __global__ void __launch_bounds__(256, 2) attn_tc_kernel(AttnParams p, uint8_t* 
         named_bar_sync(2, 128);                      // every row's P is in TMEM
         if (tid == 0) {
           tc_fence_after();
-          const uint32_t vb = sbase + st_off + st * AT_STAGE_BYTES + AT_TILE_BYTES;
+          const uint32_t vb = sbase + st_off + st * AT_STAGE_BYTES + AT_K_BYTES;
 #pragma unroll
           for (int ks = 0; ks < AT_KT / 8; ++ks) {
             const uint64_t bdesc = umma_desc_k128(vb + (ks >> 2) * 4096 + (ks & 3) * 32);
@@ -390,8 +426,10 @@ inline int attn_tc_launch(const AttnParams& p, uint8_t* scratch, cudaStream_t s,
     }
     configured = true;
   }
+  const int nqt = (p.sm.S + AT_QT - 1) / AT_QT;
   long long blocks = p.sm.num_seq * kH;
-  attn_tc_kernel<<<(unsigned)blocks, 256, AT_SMEM_BYTES, s>>>(p, scratch);
+  attn_prep_kernel<<<(unsigned)blocks, 256, 0, s>>>(p, scratch);
+  attn_tc_kernel<<<(unsigned)(blocks * nqt), AT_THREADS, AT_SMEM_BYTES, s>>>(p, scratch);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     if (err) *err = std::string("attn_tc launch: ") + cudaGetErrorString(e);

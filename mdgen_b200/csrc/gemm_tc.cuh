@@ -255,6 +255,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     const int half = (warp - 4) >> 2;                       // which 96-column half of the tile
     float* stg = reinterpret_cast<float*>(sgen + TC_STAGES * TC_STAGE_BYTES + 256) + (warp - 4) * 32 * TC_EPI_PITCH;
     const int rr0 = lane >> 3, c4 = lane & 7;
+    // gate rows: base of the current step's modulation row (read once), + b * bstride rows per sample
+    const float* gate_base = nullptr;
+    if (MODE == EPI_RESID_GATE)
+      gate_base = ep.mod.base + (size_t)(ep.mod.step_ptr ? *ep.mod.step_ptr : 0) * ep.mod.width + ep.gate_off;
     uint32_t it = 0;
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
       const uint32_t buf = it & 1u, bphase = (it >> 1) & 1u;
@@ -264,6 +268,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       tc_fence_after();
 #pragma unroll 1
       for (int c0 = 0; c0 < TC_BN / 2; c0 += 32) {
+        // residual rows of this chunk are prefetched first (8 independent 128-bit loads per lane) so
+        // their DRAM/L2 latency overlaps the TMEM load and the shared-memory transpose
+        float4 res[8];
+        if (MODE == EPI_RESID_GATE || MODE == EPI_RESID) {
+#pragma unroll
+          for (int itr = 0; itr < 8; ++itr) {
+            const long long m = mbase + itr * 4 + rr0;
+            res[itr] = (m < M) ? *reinterpret_cast<const float4*>(ep.resid + (size_t)m * ep.ldo + n0 + c0 + 4 * c4)
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
         uint32_t v[32];
         tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * TC_BN + half * (TC_BN / 2) + c0, v);
         tc_ld_wait();
@@ -274,16 +289,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
               make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
                           __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
         __syncwarp();
+        const int n = n0 + c0 + 4 * c4;
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ep.bias) bias4 = *reinterpret_cast<const float4*>(ep.bias + n);
         // 8 lanes cover one 128-byte row segment; a warp instruction covers 4 rows
 #pragma unroll
         for (int itr = 0; itr < 8; ++itr) {
           const int rr = itr * 4 + rr0;
           const long long m = mbase + rr;
-          const float4 a = *reinterpret_cast<const float4*>(stg + rr * TC_EPI_PITCH + 4 * c4);
+          float4 a = *reinterpret_cast<const float4*>(stg + rr * TC_EPI_PITCH + 4 * c4);
           if (m < M) {
-            const float* gate_row = nullptr;
-            if (MODE == EPI_RESID_GATE) gate_row = mod_row(ep.mod, m) + ep.gate_off;
-            tc_epilogue4<MODE>(ep, gate_row, m, n0 + c0 + 4 * c4, a.x, a.y, a.z, a.w);
+            a.x += bias4.x; a.y += bias4.y; a.z += bias4.z; a.w += bias4.w;
+            if (MODE == EPI_GELU) { a.x = gelu_fast(a.x); a.y = gelu_fast(a.y); a.z = gelu_fast(a.z); a.w = gelu_fast(a.w); }
+            if (MODE == EPI_RESID_GATE) {
+              const int bb = (int)(m / ep.mod.tokens_per_b) % ep.mod.bmod;
+              const float4 g = *reinterpret_cast<const float4*>(gate_base + (size_t)(bb * ep.mod.bstride) * ep.mod.width + n);
+              a.x = res[itr].x + g.x * a.x; a.y = res[itr].y + g.y * a.y;
+              a.z = res[itr].z + g.z * a.z; a.w = res[itr].w + g.w * a.w;
+            }
+            if (MODE == EPI_RESID) { a.x += res[itr].x; a.y += res[itr].y; a.z += res[itr].z; a.w += res[itr].w; }
+            if (ep.round_out) { a.x = round_tf32_fast(a.x); a.y = round_tf32_fast(a.y); a.z = round_tf32_fast(a.z); a.w = round_tf32_fast(a.w); }
+            *reinterpret_cast<float4*>(ep.out + (size_t)m * ep.ldo + n) = a;
           }
         }
         __syncwarp();

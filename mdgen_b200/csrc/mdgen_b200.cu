@@ -360,7 +360,7 @@ int attention(mdgen_handle* h, cudaStream_t s, const float* qkv, const float* ma
       h->attn_scratch_bytes = need;
     }
     if (attn_tc_launch(p, h->attn_scratch, s, &h->err)) return MDGEN_E_CUDA;
-    h->launches++;
+    h->launches += 2;
     return MDGEN_OK;
   }
 #endif
@@ -737,8 +737,6 @@ int mdgen_sample_euler(mdgen_handle* h, const float* zs, const float* t_grid, in
   if (!h || !zs || !t_grid || !x_out || K < 1) { if (h) h->err = "mdgen_sample_euler: bad argument"; return MDGEN_E_INVALID; }
   cudaStream_t s = (cudaStream_t)stream;
   TRY(prepare_call(h, s, cond, K));
-  const long long N = (long long)cond->B * cond->T * cond->L;
-  const int D = h->cfg.latent_dim;
   // time rows t_k (k < K) and fp32 step sizes dt_k = t_{k+1} - t_k (integrators.py:90; torchdiffeq)
   std::vector<float> dt(K);
   for (int k = 0; k < K; ++k) dt[k] = t_grid[k + 1] - t_grid[k];
