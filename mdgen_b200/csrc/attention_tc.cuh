@@ -2,23 +2,27 @@
 // softmax(Q K^T + key-padding) V with bias-KV token and RoPE, scores never leave the SM
 // (restates mdgen/model/mha.py:260-397; K8-K13 of SURVEY.md §2c collapse into this kernel).
 //
-// One CTA = one (sequence, head, 128-query tile); 160 threads, three CTAs per SM (128 TMEM columns and ~70 KB of
-// shared memory each), so three independent softmax warps per SM sub-partition hide each other's
-// TMEM / mbarrier latencies:
+// One CTA = one (sequence, head, 128-query tile); 160 threads, two CTAs per SM (256 TMEM columns and
+// ~95 KB of shared memory each). Inside a CTA the tensor pipe runs ahead of / behind the softmax:
+// S is double buffered in TMEM (QK^T of tile g+1 is issued before the softmax of tile g starts) and
+// O accumulates in TMEM across key tiles (P·V of tile g runs while tile g+1 is exponentiated), so
+// no MMA latency sits on the softmax critical path:
 //   (attn_prep_kernel)   : pre-pass that builds, once per (sequence, head), the UMMA-ready images of
 //                          every 96-key tile (K rotated by RoPE, V transposed, TF32-rounded,
 //                          K-major SWIZZLE_128B, plus additive key mask and |k| bound) in a global
 //                          scratch; the CTAs of all query tiles of that (sequence, head) are adjacent
 //                          in the grid, so they share those images through L2.
-//   warp 4 lane 0        : producer - one cp.async.bulk (TMA 1-D) per key tile refills a 2-stage
-//                          shared-memory ring from that scratch, for every query tile.
-//   warps 0-3  "softmax" : thread r owns query row r of the current 128-query tile == TMEM lane r.
-//                          Stages the RoPE'd Q tile, reads S from TMEM, fp32 online softmax, writes P
-//                          back over S in TMEM, accumulates O in registers. Thread 0 issues the MMAs.
+//   warp 4 lane 0        : producer - one cp.async.bulk (TMA 1-D) per key tile refills a 3-stage
+//                          shared-memory ring from that scratch.
+//   warp 5 lane 0        : the single MMA-issuing thread (tcgen05.mma + tcgen05.commit).
+//   warps 0-3  "softmax" : thread r owns query row r of the 128-query tile == TMEM lane r. Stages
+//                          the RoPE'd Q tile, reads S from TMEM, fp32 online softmax, writes P back
+//                          over S in TMEM. The four warps run decoupled: they only meet the MMA warp
+//                          through mbarriers (s_full / p_ready per S buffer), never each other.
 // Per key tile:  S[128x96] = Q·K^T    (3 x tcgen05.mma kind::tf32, K = 24 = 3 x 8, A/B from smem)
 //                P = exp2(S - m)      (softmax warps, TMEM -> regs -> TMEM, in place)
 //                O_t[128x32] = P·V    (12 x tcgen05.mma kind::tf32, A = P from TMEM, B = V^T smem)
-//                acc = acc*alpha + O_t (registers; no TMEM rescale pass)
+//                O (TMEM) += P·V; rescaled in place only when a row's softmax reference moves
 // Online softmax reference: the exact two-pass (row max, then exp) is used for a tile only when the
 // row has no reference yet or when the Cauchy-Schwarz bound |q_i|*max_j|k_j| could exceed the
 // reference by 2^100; otherwise the tile is exponentiated in a single TMEM pass against the
@@ -34,15 +38,16 @@ namespace mdgen {
 
 constexpr int AT_QT = 128;                      // queries per tile (UMMA M)
 constexpr int AT_KT = 96;                       // keys per tile (UMMA N of QK^T, K of PV)
-constexpr int AT_THREADS = 160;
+constexpr int AT_THREADS = 192;                 // 4 softmax warps + TMA producer warp + MMA issuer warp
 constexpr int AT_Q_BYTES = 128 * 128;           // Q tile: 128 rows x 128-byte pitch
 constexpr int AT_K_BYTES = AT_KT * 128;         // K tile
 constexpr int AT_VT_BYTES = (AT_KT / 32) * 4096;   // V^T: k-atoms of [32 d-rows x 32 keys]
 constexpr int AT_KM_FLOATS = 128 + 4 + 4;       // key mask | per-slice "has masked key" flags | per-slice max |k|
 constexpr int AT_IMG_BYTES = AT_K_BYTES + AT_VT_BYTES + AT_KM_FLOATS * 4;   // one staged key tile
 constexpr int AT_STAGE_BYTES = 26 * 1024;       // smem stage pitch (keeps K / V^T 1024-byte aligned)
-constexpr int AT_SMEM_BYTES = 1024 /*align*/ + AT_Q_BYTES + 2 * AT_STAGE_BYTES + 128;
-constexpr int AT_TMEM_COLS = 128;               // S/P: cols [0,96), O tile: cols [96,128)
+constexpr int AT_STAGES = 3;
+constexpr int AT_SMEM_BYTES = 1024 /*align*/ + AT_Q_BYTES + AT_STAGES * AT_STAGE_BYTES + 128;
+constexpr int AT_TMEM_COLS = 256;               // S/P double buffer: cols [0,96) [96,192); O: cols [192,224)
 
 __device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&v)[32]) {
   asm volatile(
@@ -60,6 +65,11 @@ __device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t (&v)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                : "memory");
 }
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
@@ -187,7 +197,7 @@ __global__ void __launch_bounds__(256) attn_prep_kernel(AttnParams p, uint8_t* _
   }
 }
 
-__global__ void __launch_bounds__(AT_THREADS, 3) attn_tc_kernel(AttnParams p, uint8_t* __restrict__ scratch) {
+__global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(AttnParams p, const uint8_t* __restrict__ scratch) {
   extern __shared__ uint8_t smem_raw[];
   const SeqMap& sm = p.sm;
   const uint32_t raw = smem_u32(smem_raw);
@@ -196,24 +206,27 @@ __global__ void __launch_bounds__(AT_THREADS, 3) attn_tc_kernel(AttnParams p, ui
   // carve-up
   const uint32_t q_off = 0;
   const uint32_t st_off = AT_Q_BYTES;                          // stage s: [K | V^T | mask block]
-  const uint32_t bar_off = AT_Q_BYTES + 2 * AT_STAGE_BYTES;
-  const uint32_t b_sfull = sbase + bar_off, b_ofull = b_sfull + 8;
-  auto b_kvfull = [&](int s) { return sbase + bar_off + 16 + 8 * s; };
-  auto b_kvfree = [&](int s) { return sbase + bar_off + 32 + 8 * s; };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sgen + bar_off + 48);
+  const uint32_t bar_off = AT_Q_BYTES + AT_STAGES * AT_STAGE_BYTES;
+  auto b_sfull = [&](int b) { return sbase + bar_off + 8 * b; };             // [2] MMA -> softmax
+  auto b_kvfull = [&](int s) { return sbase + bar_off + 16 + 8 * s; };       // [3] TMA -> MMA
+  auto b_kvfree = [&](int s) { return sbase + bar_off + 40 + 8 * s; };       // [3] MMA -> TMA
+  const uint32_t b_odone = sbase + bar_off + 64;                             //     MMA -> softmax (O valid)
+  auto b_pready = [&](int b) { return sbase + bar_off + 72 + 8 * b; };       // [2] softmax -> MMA
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sgen + bar_off + 88);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int S = sm.S, nkeys = S + 1;
   const int nqt = (S + AT_QT - 1) / AT_QT, nkt = (nkeys + AT_KT - 1) / AT_KT;
-  const int qt0 = blockIdx.x % nqt;                     // query tile of this CTA (fastest: the CTAs
+  const int qt = blockIdx.x % nqt;                      // query tile of this CTA (fastest: the CTAs
   const long long sh = blockIdx.x / nqt;                // sharing one set of key images run together)
   const int h = (int)(sh % kH);
   const long long s = sh / kH;
   const uint8_t* img = scratch + (size_t)sh * nkt * AT_IMG_BYTES;
 
   if (tid == 0) {
-    mbar_init(b_sfull, 1); mbar_init(b_ofull, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(b_kvfull(i), 1); mbar_init(b_kvfree(i), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(b_sfull(b), 1); mbar_init(b_pready(b), 4); }
+    mbar_init(b_odone, 1);
+    for (int i = 0; i < AT_STAGES; ++i) { mbar_init(b_kvfull(i), 1); mbar_init(b_kvfree(i), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -221,187 +234,202 @@ __global__ void __launch_bounds__(AT_THREADS, 3) attn_tc_kernel(AttnParams p, ui
                  ::"r"(smem_u32((const void*)tmem_slot)), "r"((uint32_t)AT_TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  // ---- stage the Q tile (softmax threads: one row each), RoPE'd, scaled by log2(e), TF32-rounded
+  const int r = tid;
+  const int e = qt * AT_QT + r;
+  const bool qok = (tid < 128) && e < S;
+  long long tq = 0;
+  float qnorm = 0.f;
+  if (tid < 128) {
+    tq = seq_token(sm, s, e < S ? e : S - 1);
+    float q[kHD];
+    const float4* qp = reinterpret_cast<const float4*>(p.qkv + (size_t)tq * kQKV + h * kHD);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { float4 a = qp[i]; q[4*i] = a.x; q[4*i+1] = a.y; q[4*i+2] = a.z; q[4*i+3] = a.w; }
+    const int pe = e < S ? e : S - 1;
+    rope24(q, p.cosT + pe * kHalf, p.sinT + pe * kHalf);
+    float qn2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < kHD; ++i) { q[i] = round_tf32(q[i] * 1.4426950408889634f); qn2 = fmaf(q[i], q[i], qn2); }
+    qnorm = sqrtf(qn2) * 1.001f;
+#pragma unroll
+    for (int c = 0; c < 6; ++c)
+      *reinterpret_cast<float4*>(sgen + q_off + sw128_off(r, c)) = make_float4(q[4*c], q[4*c+1], q[4*c+2], q[4*c+3]);
+    fence_async_smem();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + AT_KT;
+  const uint32_t tmem_O = tmem_base + 2 * AT_KT;
 
   if (warp == 4) {
     if (lane == 0) {
       // =============================== producer (TMA 1-D bulk copies) ===============================
-      for (int qt = qt0, g = 0; qt < qt0 + 1; ++qt) {
-        for (int kt = 0; kt < nkt; ++kt, ++g) {
-          const int st = g & 1, use = g >> 1;
-          mbar_wait_backoff(b_kvfree(st), (uint32_t)((use & 1) ^ 1));   // PV of the previous user retired
-          mbar_expect_tx(b_kvfull(st), AT_IMG_BYTES);
-          const uint32_t dst = sbase + st_off + st * AT_STAGE_BYTES;
-          const uint8_t* src = img + (size_t)kt * AT_IMG_BYTES;
-          asm volatile(
-              "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-              ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"((uint32_t)AT_IMG_BYTES), "r"(b_kvfull(st))
-              : "memory");
-        }
+      for (int g = 0; g < nkt; ++g) {
+        const int st = g % AT_STAGES, use = g / AT_STAGES;
+        mbar_wait_backoff(b_kvfree(st), (uint32_t)((use & 1) ^ 1));   // PV of the previous user retired
+        mbar_expect_tx(b_kvfull(st), AT_IMG_BYTES);
+        const uint32_t dst = sbase + st_off + st * AT_STAGE_BYTES;
+        const uint8_t* src = img + (size_t)g * AT_IMG_BYTES;
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+            ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"((uint32_t)AT_IMG_BYTES), "r"(b_kvfull(st))
+            : "memory");
       }
     }
-  } else {
-    // =============================== softmax + MMA issue ===============================
-    const int r = tid;                              // query row in tile == TMEM lane
-    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
-    constexpr uint32_t idesc_qk = umma_idesc_tf32(AT_QT, AT_KT);
-    constexpr uint32_t idesc_pv = umma_idesc_tf32(AT_QT, 32);
-    const float LOG2E = 1.4426950408889634f;
-    uint32_t ph_s = 0, ph_o = 0;
-    for (int qt = qt0, g = 0; qt < qt0 + 1; ++qt) {
-      // ---- stage the Q tile (all earlier MMAs reading it have completed: last o_full was waited)
-      const int e = qt * AT_QT + r;
-      const bool qok = e < S;
-      const long long tq = seq_token(sm, s, qok ? e : S - 1);
-      float qnorm;
-      {
-        float q[kHD];
-        const float4* qp = reinterpret_cast<const float4*>(p.qkv + (size_t)tq * kQKV + h * kHD);
-#pragma unroll
-        for (int i = 0; i < 6; ++i) { float4 a = qp[i]; q[4*i] = a.x; q[4*i+1] = a.y; q[4*i+2] = a.z; q[4*i+3] = a.w; }
-        const int pe = qok ? e : S - 1;
-        rope24(q, p.cosT + pe * kHalf, p.sinT + pe * kHalf);
-        float qn2 = 0.f;
-#pragma unroll
-        for (int i = 0; i < kHD; ++i) { q[i] = round_tf32(q[i] * LOG2E); qn2 = fmaf(q[i], q[i], qn2); }
-        qnorm = sqrtf(qn2) * 1.001f;
-#pragma unroll
-        for (int c = 0; c < 6; ++c)
-          *reinterpret_cast<float4*>(sgen + q_off + sw128_off(r, c)) = make_float4(q[4*c], q[4*c+1], q[4*c+2], q[4*c+3]);
-      }
-      fence_async_smem();
-      named_bar_sync(2, 128);
-      float acc[kHD];
-#pragma unroll
-      for (int i = 0; i < kHD; ++i) acc[i] = 0.f;
-      float m_run = -INFINITY, l_run = 0.f;
-
+  } else if (warp == 5) {
+    if (lane == 0) {
+      // =============================== MMA issuer (one thread) ===============================
+      constexpr uint32_t idesc_qk = umma_idesc_tf32(AT_QT, AT_KT);
+      constexpr uint32_t idesc_pv = umma_idesc_tf32(AT_QT, 32);
+      // S[gg & 1] = Q · K(gg)^T
       auto issue_qk = [&](int gg) {
-        const int st = gg & 1, use = gg >> 1;
+        const int st = gg % AT_STAGES, use = gg / AT_STAGES;
         mbar_wait(b_kvfull(st), (uint32_t)(use & 1));
         tc_fence_after();
         const uint64_t adesc = umma_desc_k128(sbase + q_off);
         const uint64_t bdesc = umma_desc_k128(sbase + st_off + st * AT_STAGE_BYTES);
+        const uint32_t tS = tmem_base + (gg & 1) * AT_KT;
 #pragma unroll
         for (int k = 0; k < 3; ++k)
-          tc_mma_tf32(tmem_S, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_qk, (uint32_t)(k != 0));
-        tc_commit(b_sfull);
+          tc_mma_tf32(tS, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_qk, (uint32_t)(k != 0));
+        tc_commit(b_sfull(gg & 1));
       };
-      if (tid == 0) issue_qk(g);
-
-      for (int kt = 0; kt < nkt; ++kt, ++g) {
-        const int st = g & 1;
-        mbar_wait(b_sfull, ph_s); ph_s ^= 1u;
+      issue_qk(0);
+      if (nkt > 1) issue_qk(1);
+      for (int g = 0; g < nkt; ++g) {
+        const int st = g % AT_STAGES, buf = g & 1;
+        mbar_wait(b_pready(buf), (uint32_t)((g >> 1) & 1));   // all four softmax warps wrote P(g)
         tc_fence_after();
-        const float* kmask = reinterpret_cast<const float*>(sgen + st_off + st * AT_STAGE_BYTES + AT_K_BYTES + AT_VT_BYTES);
-        const int4 fl = *reinterpret_cast<const int4*>(kmask + 128);      // one flag per 32-key slice
-        const bool masked = (fl.x | fl.y | fl.z) != 0;
-        const float4 kn = *reinterpret_cast<const float4*>(kmask + 132);  // max |k| per slice
-        const float bound = qnorm * fmaxf(kn.x, fmaxf(kn.y, kn.z));       // >= every score of this row & tile
-        // exact two-pass only when this row has no reference yet or the bound could overflow exp2
-        const bool need_exact = __any_sync(0xffffffffu, (m_run == -INFINITY) || (bound - m_run > 100.f));
-        float m_new = m_run;
-        if (need_exact) {
-          // ---- pass 1: exact row max of this tile (chunk c+1 in flight while chunk c is reduced)
-          float tmax = -INFINITY;
-          uint32_t va[16], vb[16];
-          tc_ld16(tmem_S + lane_addr, va);
-          tc_ld_wait();
+        const uint32_t tmem_S = tmem_base + buf * AT_KT;
+        const uint32_t vb = sbase + st_off + st * AT_STAGE_BYTES + AT_K_BYTES;
 #pragma unroll
-          for (int cc = 0; cc < AT_KT / 16; ++cc) {
-            uint32_t (&cur)[16] = (cc & 1) ? vb : va;
-            uint32_t (&nxt)[16] = (cc & 1) ? va : vb;
-            if (cc < AT_KT / 16 - 1) tc_ld16(tmem_S + lane_addr + (cc + 1) * 16, nxt);
-            if (masked) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) tmax = fmaxf(tmax, __uint_as_float(cur[i]) + kmask[cc * 16 + i]);
-            } else {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) tmax = fmaxf(tmax, __uint_as_float(cur[i]));
-            }
-            if (cc < AT_KT / 16 - 1) tc_ld_wait();
-          }
-          m_new = fmaxf(m_run, tmax);
+        for (int ks = 0; ks < AT_KT / 8; ++ks) {
+          const uint64_t bdesc = umma_desc_k128(vb + (ks >> 2) * 4096 + (ks & 3) * 32);
+          tc_mma_tf32_ts(tmem_O, tmem_S + 8 * ks, bdesc, idesc_pv, (uint32_t)((g | ks) != 0));
         }
-        const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-        const float alpha = ex2f(m_run - m_use);      // 1 when the reference is unchanged
-        // ---- P = exp2(S - m), written back over S. The denominator sums the exact fp32 p; the
-        // numerator operand is rounded to TF32 by adding half an ulp (the MMA truncates the low 13
-        // mantissa bits), so its rounding error is zero-mean.
-        float lsum = 0.f;
-        {
-          uint32_t va[16], vb[16];
-          tc_ld16(tmem_S + lane_addr, va);
-          tc_ld_wait();
-#pragma unroll
-          for (int cc = 0; cc < AT_KT / 16; ++cc) {
-            uint32_t (&cur)[16] = (cc & 1) ? vb : va;
-            uint32_t (&nxt)[16] = (cc & 1) ? va : vb;
-            if (cc < AT_KT / 16 - 1) tc_ld16(tmem_S + lane_addr + (cc + 1) * 16, nxt);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float x = __uint_as_float(cur[i]);
-              if (masked) x += kmask[cc * 16 + i];
-              float pv = ex2f(x - m_use);
-              lsum += pv;
-              cur[i] = __float_as_uint(pv) + 0x1000u;
-            }
-            if (cc < AT_KT / 16 - 1) tc_ld_wait();
-            tc_st16(tmem_S + lane_addr + cc * 16, cur);
-          }
-        }
-        tc_st_wait();
-        l_run = l_run * alpha + lsum;
-        m_run = m_new;
-        tc_fence_before();
-        named_bar_sync(2, 128);                      // every row's P is in TMEM
-        if (tid == 0) {
-          tc_fence_after();
-          const uint32_t vb = sbase + st_off + st * AT_STAGE_BYTES + AT_K_BYTES;
-#pragma unroll
-          for (int ks = 0; ks < AT_KT / 8; ++ks) {
-            const uint64_t bdesc = umma_desc_k128(vb + (ks >> 2) * 4096 + (ks & 3) * 32);
-            tc_mma_tf32_ts(tmem_O, tmem_S + 8 * ks, bdesc, idesc_pv, (uint32_t)(ks != 0));
-          }
-          tc_commit(b_ofull);
-          tc_commit(b_kvfree(st));                   // K/V stage reusable once the PV MMAs retire
-          if (kt + 1 < nkt) issue_qk(g + 1);         // next S (in order after PV on the tensor pipe)
-        }
-        // ---- O tile -> registers
-        mbar_wait(b_ofull, ph_o); ph_o ^= 1u;
-        tc_fence_after();
-        {
-          uint32_t o0[8], o1[8], o2[8];
-          tc_ld8(tmem_O + lane_addr + 0, o0);
-          tc_ld8(tmem_O + lane_addr + 8, o1);
-          tc_ld8(tmem_O + lane_addr + 16, o2);
-          tc_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            acc[i] = fmaf(acc[i], alpha, __uint_as_float(o0[i]));
-            acc[8 + i] = fmaf(acc[8 + i], alpha, __uint_as_float(o1[i]));
-            acc[16 + i] = fmaf(acc[16 + i], alpha, __uint_as_float(o2[i]));
-          }
-        }
-        tc_fence_before();
+        tc_commit(b_kvfree(st));                   // K/V stage reusable once the PV MMAs retire
+        tc_commit(b_odone);
+        if (g + 2 < nkt) issue_qk(g + 2);          // refill this S buffer (in order after P·V(g))
       }
-      // ---- write this query tile's output rows
+    }
+  } else if (warp < 4) {
+    // =============================== softmax ===============================
+    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int g = 0; g < nkt; ++g) {
+      const int st = g % AT_STAGES, buf = g & 1;
+      const uint32_t tmem_S = tmem_base + buf * AT_KT;
+      mbar_wait(b_sfull(buf), (uint32_t)((g >> 1) & 1));
+      tc_fence_after();
+      const float* kmask = reinterpret_cast<const float*>(sgen + st_off + st * AT_STAGE_BYTES + AT_K_BYTES + AT_VT_BYTES);
+      const int4 fl = *reinterpret_cast<const int4*>(kmask + 128);      // one flag per 32-key slice
+      const bool masked = (fl.x | fl.y | fl.z) != 0;
+      const float4 kn = *reinterpret_cast<const float4*>(kmask + 132);  // max |k| per slice
+      const float bound = qnorm * fmaxf(kn.x, fmaxf(kn.y, kn.z));       // >= every score of this row & tile
+      // exact two-pass only when this row has no reference yet or the bound could overflow exp2
+      const bool need_exact = __any_sync(0xffffffffu, (m_run == -INFINITY) || (bound - m_run > 100.f));
+      float m_new = m_run;
+      if (need_exact) {
+        // ---- pass 1: exact row max of this tile (chunk c+1 in flight while chunk c is reduced)
+        float tmax = -INFINITY;
+        uint32_t va[16], vb[16];
+        tc_ld16(tmem_S + lane_addr, va);
+        tc_ld_wait();
+#pragma unroll
+        for (int cc = 0; cc < AT_KT / 16; ++cc) {
+          uint32_t (&cur)[16] = (cc & 1) ? vb : va;
+          uint32_t (&nxt)[16] = (cc & 1) ? va : vb;
+          if (cc < AT_KT / 16 - 1) tc_ld16(tmem_S + lane_addr + (cc + 1) * 16, nxt);
+          if (masked) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) tmax = fmaxf(tmax, __uint_as_float(cur[i]) + kmask[cc * 16 + i]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) tmax = fmaxf(tmax, __uint_as_float(cur[i]));
+          }
+          if (cc < AT_KT / 16 - 1) tc_ld_wait();
+        }
+        m_new = fmaxf(m_run, tmax);
+      }
+      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+      const float alpha = ex2f(m_run - m_use);      // 1 when the reference is unchanged
+      // ---- P = exp2(S - m), written back over S. The denominator sums the exact fp32 p; the
+      // numerator operand is rounded to TF32 by adding half an ulp (the MMA truncates the low 13
+      // mantissa bits), so its rounding error is zero-mean.
+      float lsum = 0.f;
+      {
+        uint32_t va[16], vb[16];
+        tc_ld16(tmem_S + lane_addr, va);
+        tc_ld_wait();
+#pragma unroll
+        for (int cc = 0; cc < AT_KT / 16; ++cc) {
+          uint32_t (&cur)[16] = (cc & 1) ? vb : va;
+          uint32_t (&nxt)[16] = (cc & 1) ? va : vb;
+          if (cc < AT_KT / 16 - 1) tc_ld16(tmem_S + lane_addr + (cc + 1) * 16, nxt);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float x = __uint_as_float(cur[i]);
+            if (masked) x += kmask[cc * 16 + i];
+            float pv = ex2f(x - m_use);
+            lsum += pv;
+            cur[i] = __float_as_uint(pv) + 0x1000u;
+          }
+          if (cc < AT_KT / 16 - 1) tc_ld_wait();
+          tc_st16(tmem_S + lane_addr + cc * 16, cur);
+        }
+      }
+      // ---- the softmax reference of some row in this warp moved: rescale its O accumulator in TMEM
+      // (rare: the first tile has nothing to rescale, later tiles keep the reference unless the
+      //  overflow bound trips)
+      if (g > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
+        mbar_wait(b_odone, (uint32_t)((g - 1) & 1));   // P·V of every earlier tile has retired
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          uint32_t o[8];
+          tc_ld8(tmem_O + lane_addr + 8 * c, o);
+          tc_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tc_st8(tmem_O + lane_addr + 8 * c, o);
+        }
+      }
+      tc_st_wait();
+      l_run = l_run * alpha + lsum;
+      m_run = m_new;
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(b_pready(buf));   // this warp's 32 rows of P (and rescaled O) are in TMEM
+    }
+    // ---- epilogue: O / l -> global
+    mbar_wait(b_odone, (uint32_t)((nkt - 1) & 1));
+    tc_fence_after();
+    {
+      uint32_t o0[8], o1[8], o2[8];
+      tc_ld8(tmem_O + lane_addr + 0, o0);
+      tc_ld8(tmem_O + lane_addr + 8, o1);
+      tc_ld8(tmem_O + lane_addr + 16, o2);
+      tc_ld_wait();
       if (qok) {
         const float inv = 1.0f / l_run;
+        float acc[kHD];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          acc[i] = __uint_as_float(o0[i]) * inv; acc[8 + i] = __uint_as_float(o1[i]) * inv;
+          acc[16 + i] = __uint_as_float(o2[i]) * inv;
+        }
         float4* op = reinterpret_cast<float4*>(p.out + (size_t)tq * kC + h * kHD);
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
-          float4 o = make_float4(acc[4*i] * inv, acc[4*i+1] * inv, acc[4*i+2] * inv, acc[4*i+3] * inv);
+          float4 o = make_float4(acc[4*i], acc[4*i+1], acc[4*i+2], acc[4*i+3]);
           if (p.round_out) { o.x = round_tf32_fast(o.x); o.y = round_tf32_fast(o.y); o.z = round_tf32_fast(o.z); o.w = round_tf32_fast(o.w); }
           op[i] = o;
         }
       }
-      named_bar_sync(2, 128);   // all rows done with TMEM O / smem Q before the next tile restages Q
     }
+    tc_fence_before();
   }
   tc_fence_before();
   __syncthreads();
