@@ -207,6 +207,7 @@ def main():
     import torch
     import torch.distributed as dist
     from mdgen_b200.config import default_args
+    from mdgen_b200.dist import gather_counts, max_over_ranks, rank_seed
     from mdgen_b200.synthetic import (euler_time_grid, synthetic_batch, synthetic_noise,
                                       synthetic_state_dict)
     from mdgen_b200.wrapper import NewMDGenWrapper
@@ -229,10 +230,10 @@ def main():
         eng.set_option("use_tc", a.use_tc)
     D = m.latent_dim
     # every rank samples its own shard of independent trajectories (different seeds per rank)
-    hbatch = synthetic_batch(B, T, L, seed=1 + rank, vary_frames=False)
+    hbatch = synthetic_batch(B, T, L, seed=rank_seed(1, rank), vary_frames=False)
     hbatch = {k: v.pin_memory() for k, v in hbatch.items()}
     dbatch = {k: v.to(dev, non_blocking=True) for k, v in hbatch.items()}
-    zs = synthetic_noise(B, T, L, D, seed=2 + rank).to(dev)
+    zs = synthetic_noise(B, T, L, D, seed=rank_seed(2, rank)).to(dev)
     grid = euler_time_grid(K)
     prep = m.prep_batch(dbatch)
     kw = prep["model_kwargs"]
@@ -252,11 +253,9 @@ def main():
             fn()
         e1.record()
         torch.cuda.synchronize()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms = max_over_ranks(e0.elapsed_time(e1), device=dev)
         sync_all()
-        return float(ms.item())
+        return ms
 
     def hot():
         return m.model.sample_euler(zs, grid, **kw)
@@ -275,7 +274,8 @@ def main():
     clk = clocks.stop()
     launches = eng.launch_count - l0
     ms_per_step = ms / a.steps
-    value = world * B * T / (ms_per_step / 1e3)
+    total_traj = sum(gather_counts(B, device=dev))          # trajectories sampled per step, all ranks
+    value = total_traj * T / (ms_per_step / 1e3)
 
     e2e = None
     if not a.no_e2e:
@@ -283,7 +283,7 @@ def main():
         ms_e = timed(e2e_call, max(1, min(a.steps, 2))) / max(1, min(a.steps, 2))
         h2d = sum(v.numel() * v.element_size() for v in hbatch.values())
         d2h = B * T * L * 14 * 3 * 4
-        e2e = {"value": world * B * T / (ms_e / 1e3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
+        e2e = {"value": total_traj * T / (ms_e / 1e3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": ms_e,
                "api": "NewMDGenWrapper.inference(batch) on pinned host tensors -> atom14.cpu()"}
 
