@@ -110,6 +110,75 @@ __global__ void __launch_bounds__(128) attn_small_kernel(AttnParams p) {
   }
 }
 
+// ---- S == 4 (tetrapeptide residue attention, mha_l at crop 4): every q/k/v row is loaded from HBM
+// exactly once. Lane = (token-in-sequence tl, head-in-octet hh): a warp owns one sequence x 8 heads;
+// each lane rotates its own q and k once and the 4x5 attention exchanges k/v through warp shuffles.
+__global__ void __launch_bounds__(256) attn_l4_kernel(AttnParams p) {
+  const SeqMap& sm = p.sm;
+  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // warp = (sequence, head octet)
+  const int lane = threadIdx.x & 31;
+  if (w >= sm.num_seq * 2) return;
+  const long long s = w >> 1;
+  const int tl = lane >> 3, h = (int)(w & 1) * 8 + (lane & 7);
+  const long long tok = seq_token(sm, s, tl);
+  float q[kHD], k[kHD], v[kHD];
+  {
+    const float4* qp = reinterpret_cast<const float4*>(p.qkv + (size_t)tok * kQKV + h * kHD);
+    const float4* kp = reinterpret_cast<const float4*>(p.qkv + (size_t)tok * kQKV + kC + h * kHD);
+    const float4* vp = reinterpret_cast<const float4*>(p.qkv + (size_t)tok * kQKV + 2 * kC + h * kHD);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      float4 a = qp[i]; q[4*i] = a.x; q[4*i+1] = a.y; q[4*i+2] = a.z; q[4*i+3] = a.w;
+      float4 b = kp[i]; k[4*i] = b.x; k[4*i+1] = b.y; k[4*i+2] = b.z; k[4*i+3] = b.w;
+      float4 c = vp[i]; v[4*i] = c.x; v[4*i+1] = c.y; v[4*i+2] = c.z; v[4*i+3] = c.w;
+    }
+    rope24(q, p.cosT + tl * kHalf, p.sinT + tl * kHalf);
+    rope24(k, p.cosT + tl * kHalf, p.sinT + tl * kHalf);
+  }
+  const float valid = (p.mask == nullptr || p.mask[tok] != 0.f) ? 1.f : 0.f;
+  // scores against the 4 sibling keys + the bias key (position 4)
+  float sc[5];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float d = 0.f;
+#pragma unroll
+    for (int i = 0; i < kHD; ++i) d = fmaf(q[i], __shfl_sync(0xffffffffu, k[i], j * 8 + (lane & 7)), d);
+    float ok = __shfl_sync(0xffffffffu, valid, j * 8 + (lane & 7));
+    sc[j] = ok != 0.f ? d : -INFINITY;
+  }
+  float bk[kHD];
+#pragma unroll
+  for (int i = 0; i < kHD; ++i) bk[i] = p.bias_k[h * kHD + i];
+  rope24(bk, p.cosT + 4 * kHalf, p.sinT + 4 * kHalf);
+  {
+    float d = 0.f;
+#pragma unroll
+    for (int i = 0; i < kHD; ++i) d = fmaf(q[i], bk[i], d);
+    sc[4] = d;
+  }
+  float m = sc[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) m = fmaxf(m, sc[j]);
+  float l = 0.f;
+#pragma unroll
+  for (int j = 0; j < 5; ++j) { sc[j] = __expf(sc[j] - m); l += sc[j]; }
+  const float inv = 1.0f / l;
+  float o[kHD];
+#pragma unroll
+  for (int i = 0; i < kHD; ++i) o[i] = sc[4] * p.bias_v[h * kHD + i];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int i = 0; i < kHD; ++i) o[i] = fmaf(sc[j], __shfl_sync(0xffffffffu, v[i], j * 8 + (lane & 7)), o[i]);
+  float4* op = reinterpret_cast<float4*>(p.out + (size_t)tok * kC + h * kHD);
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    float4 r = make_float4(o[4*i] * inv, o[4*i+1] * inv, o[4*i+2] * inv, o[4*i+3] * inv);
+    if (p.round_out) { r.x = round_tf32_fast(r.x); r.y = round_tf32_fast(r.y); r.z = round_tf32_fast(r.z); r.w = round_tf32_fast(r.w); }
+    op[i] = r;
+  }
+}
+
 // ---- long sequences: block = (query tile of 256, head, sequence); 128 threads x 2 queries each;
 // K/V tiles of 32 keys staged (and rotated) in shared memory and broadcast to all threads.
 constexpr int AF_QT = 256;   // queries per block

@@ -14,11 +14,12 @@
 //                          in the grid, so they share those images through L2.
 //   warp 4 lane 0        : producer - one cp.async.bulk (TMA 1-D) per key tile refills a 3-stage
 //                          shared-memory ring from that scratch.
-//   warp 5 lane 0        : the single MMA-issuing thread (tcgen05.mma + tcgen05.commit).
-//   warps 0-3  "softmax" : thread r owns query row r of the 128-query tile == TMEM lane r. Stages
-//                          the RoPE'd Q tile, reads S from TMEM, fp32 online softmax, writes P back
-//                          over S in TMEM. The four warps run decoupled: they only meet the MMA warp
-//                          through mbarriers (s_full / p_ready per S buffer), never each other.
+//   warp 9 lane 0        : the single MMA-issuing thread (tcgen05.mma + tcgen05.commit).
+//   warps 0-7  "softmax" : warp w owns the 32 query rows of TMEM lane quarter (w & 3) and the column
+//                          half (w >> 2) of every S tile: reads S from TMEM, fp32 online softmax,
+//                          writes P back over S in TMEM. Warps run decoupled: they meet the MMA warp
+//                          through mbarriers (s_full / p_ready per S buffer); the two warps sharing
+//                          a row only exchange data on the rare exact-max path and in the epilogue.
 // Per key tile:  S[128x96] = Q·K^T    (3 x tcgen05.mma kind::tf32, K = 24 = 3 x 8, A/B from smem)
 //                P = exp2(S - m)      (softmax warps, TMEM -> regs -> TMEM, in place)
 //                O_t[128x32] = P·V    (12 x tcgen05.mma kind::tf32, A = P from TMEM, B = V^T smem)
@@ -38,7 +39,8 @@ namespace mdgen {
 
 constexpr int AT_QT = 128;                      // queries per tile (UMMA M)
 constexpr int AT_KT = 96;                       // keys per tile (UMMA N of QK^T, K of PV)
-constexpr int AT_THREADS = 192;                 // 4 softmax warps + TMA producer warp + MMA issuer warp
+constexpr int AT_THREADS = 320;                 // 8 softmax warps + TMA producer warp + MMA issuer warp
+constexpr int AT_HALF = AT_KT / 2;              // columns of an S tile handled by one softmax warp
 constexpr int AT_Q_BYTES = 128 * 128;           // Q tile: 128 rows x 128-byte pitch
 constexpr int AT_K_BYTES = AT_KT * 128;         // K tile
 constexpr int AT_VT_BYTES = (AT_KT / 32) * 4096;   // V^T: k-atoms of [32 d-rows x 32 keys]
@@ -46,7 +48,7 @@ constexpr int AT_KM_FLOATS = 128 + 4 + 4;       // key mask | per-slice "has mas
 constexpr int AT_IMG_BYTES = AT_K_BYTES + AT_VT_BYTES + AT_KM_FLOATS * 4;   // one staged key tile
 constexpr int AT_STAGE_BYTES = 26 * 1024;       // smem stage pitch (keeps K / V^T 1024-byte aligned)
 constexpr int AT_STAGES = 3;
-constexpr int AT_SMEM_BYTES = 1024 /*align*/ + AT_Q_BYTES + AT_STAGES * AT_STAGE_BYTES + 128;
+constexpr int AT_SMEM_BYTES = 1024 /*align*/ + AT_Q_BYTES + AT_STAGES * AT_STAGE_BYTES + 128 /*barriers*/ + 4 * 512 /*row exchange*/;
 constexpr int AT_TMEM_COLS = 256;               // S/P double buffer: cols [0,96) [96,192); O: cols [192,224)
 
 __device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&v)[32]) {
@@ -213,6 +215,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(AttnParams p, co
   const uint32_t b_odone = sbase + bar_off + 64;                             //     MMA -> softmax (O valid)
   auto b_pready = [&](int b) { return sbase + bar_off + 72 + 8 * b; };       // [2] softmax -> MMA
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sgen + bar_off + 88);
+  float* xch = reinterpret_cast<float*>(sgen + bar_off + 128);   // [4][128]: qnorm | max half0 | max half1 | l half1
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int S = sm.S, nkeys = S + 1;
@@ -224,7 +227,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(AttnParams p, co
   const uint8_t* img = scratch + (size_t)sh * nkt * AT_IMG_BYTES;
 
   if (tid == 0) {
-    for (int b = 0; b < 2; ++b) { mbar_init(b_sfull(b), 1); mbar_init(b_pready(b), 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(b_sfull(b), 1); mbar_init(b_pready(b), 8); }
     mbar_init(b_odone, 1);
     for (int i = 0; i < AT_STAGES; ++i) { mbar_init(b_kvfull(i), 1); mbar_init(b_kvfree(i), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -252,6 +255,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(AttnParams p, co
 #pragma unroll
     for (int i = 0; i < kHD; ++i) { q[i] = round_tf32(q[i] * 1.4426950408889634f); qn2 = fmaf(q[i], q[i], qn2); }
     qnorm = sqrtf(qn2) * 1.001f;
+    xch[r] = qnorm;
 #pragma unroll
     for (int c = 0; c < 6; ++c)
       *reinterpret_cast<float4*>(sgen + q_off + sw128_off(r, c)) = make_float4(q[4*c], q[4*c+1], q[4*c+2], q[4*c+3]);
@@ -263,7 +267,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(AttnParams p, co
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_O = tmem_base + 2 * AT_KT;
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       // =============================== producer (TMA 1-D bulk copies) ===============================
       for (int g = 0; g < nkt; ++g) {
@@ -278,7 +282,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(AttnParams p, co
             : "memory");
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     if (lane == 0) {
       // =============================== MMA issuer (one thread) ===============================
       constexpr uint32_t idesc_qk = umma_idesc_tf32(AT_QT, AT_KT);
@@ -300,7 +304,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(AttnParams p, co
       if (nkt > 1) issue_qk(1);
       for (int g = 0; g < nkt; ++g) {
         const int st = g % AT_STAGES, buf = g & 1;
-        mbar_wait(b_pready(buf), (uint32_t)((g >> 1) & 1));   // all four softmax warps wrote P(g)
+        mbar_wait(b_pready(buf), (uint32_t)((g >> 1) & 1));   // all eight softmax warps wrote P(g)
         tc_fence_after();
         const uint32_t tmem_S = tmem_base + buf * AT_KT;
         const uint32_t vb = sbase + st_off + st * AT_STAGE_BYTES + AT_K_BYTES;
@@ -314,43 +318,54 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(AttnParams p, co
         if (g + 2 < nkt) issue_qk(g + 2);          // refill this S buffer (in order after P·V(g))
       }
     }
-  } else if (warp < 4) {
+  } else if (warp < 8) {
     // =============================== softmax ===============================
-    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
-    float m_run = -INFINITY, l_run = 0.f;
+    const int qq = warp & 3, hf = warp >> 2;         // TMEM lane quarter / column half
+    const int row = qq * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(qq * 32) << 16;
+    const int c_lo = hf * AT_HALF;                   // first S column of this warp
+    const float qn = xch[row];
+    const int e2 = qt * AT_QT + row;
+    const bool qok2 = e2 < S;
+    float m_run = -INFINITY, l_run = 0.f;            // l_run: this warp's column half only
     for (int g = 0; g < nkt; ++g) {
       const int st = g % AT_STAGES, buf = g & 1;
-      const uint32_t tmem_S = tmem_base + buf * AT_KT;
+      const uint32_t tmem_S = tmem_base + buf * AT_KT + c_lo;
       mbar_wait(b_sfull(buf), (uint32_t)((g >> 1) & 1));
       tc_fence_after();
       const float* kmask = reinterpret_cast<const float*>(sgen + st_off + st * AT_STAGE_BYTES + AT_K_BYTES + AT_VT_BYTES);
       const int4 fl = *reinterpret_cast<const int4*>(kmask + 128);      // one flag per 32-key slice
       const bool masked = (fl.x | fl.y | fl.z) != 0;
       const float4 kn = *reinterpret_cast<const float4*>(kmask + 132);  // max |k| per slice
-      const float bound = qnorm * fmaxf(kn.x, fmaxf(kn.y, kn.z));       // >= every score of this row & tile
+      const float bound = qn * fmaxf(kn.x, fmaxf(kn.y, kn.z));          // >= every score of this row & tile
       // exact two-pass only when this row has no reference yet or the bound could overflow exp2
+      // (identical decision in both warps of a row pair: same m_run, same bound)
       const bool need_exact = __any_sync(0xffffffffu, (m_run == -INFINITY) || (bound - m_run > 100.f));
       float m_new = m_run;
       if (need_exact) {
-        // ---- pass 1: exact row max of this tile (chunk c+1 in flight while chunk c is reduced)
+        // ---- pass 1: exact row max over this warp's columns, then exchange with the partner warp
         float tmax = -INFINITY;
         uint32_t va[16], vb[16];
         tc_ld16(tmem_S + lane_addr, va);
         tc_ld_wait();
 #pragma unroll
-        for (int cc = 0; cc < AT_KT / 16; ++cc) {
+        for (int cc = 0; cc < AT_HALF / 16; ++cc) {
           uint32_t (&cur)[16] = (cc & 1) ? vb : va;
           uint32_t (&nxt)[16] = (cc & 1) ? va : vb;
-          if (cc < AT_KT / 16 - 1) tc_ld16(tmem_S + lane_addr + (cc + 1) * 16, nxt);
+          if (cc < AT_HALF / 16 - 1) tc_ld16(tmem_S + lane_addr + (cc + 1) * 16, nxt);
           if (masked) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) tmax = fmaxf(tmax, __uint_as_float(cur[i]) + kmask[cc * 16 + i]);
+            for (int i = 0; i < 16; ++i) tmax = fmaxf(tmax, __uint_as_float(cur[i]) + kmask[c_lo + cc * 16 + i]);
           } else {
 #pragma unroll
             for (int i = 0; i < 16; ++i) tmax = fmaxf(tmax, __uint_as_float(cur[i]));
           }
-          if (cc < AT_KT / 16 - 1) tc_ld_wait();
+          if (cc < AT_HALF / 16 - 1) tc_ld_wait();
         }
+        xch[128 * (1 + hf) + row] = tmax;
+        named_bar_sync(3 + qq, 64);                  // the two warps of this lane quarter
+        tmax = fmaxf(tmax, xch[128 * (2 - hf) + row]);
+        named_bar_sync(3 + qq, 64);                  // partner has read before the slot is reused
         m_new = fmaxf(m_run, tmax);
       }
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
@@ -364,26 +379,26 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(AttnParams p, co
         tc_ld16(tmem_S + lane_addr, va);
         tc_ld_wait();
 #pragma unroll
-        for (int cc = 0; cc < AT_KT / 16; ++cc) {
+        for (int cc = 0; cc < AT_HALF / 16; ++cc) {
           uint32_t (&cur)[16] = (cc & 1) ? vb : va;
           uint32_t (&nxt)[16] = (cc & 1) ? va : vb;
-          if (cc < AT_KT / 16 - 1) tc_ld16(tmem_S + lane_addr + (cc + 1) * 16, nxt);
+          if (cc < AT_HALF / 16 - 1) tc_ld16(tmem_S + lane_addr + (cc + 1) * 16, nxt);
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             float x = __uint_as_float(cur[i]);
-            if (masked) x += kmask[cc * 16 + i];
+            if (masked) x += kmask[c_lo + cc * 16 + i];
             float pv = ex2f(x - m_use);
             lsum += pv;
             cur[i] = __float_as_uint(pv) + 0x1000u;
           }
-          if (cc < AT_KT / 16 - 1) tc_ld_wait();
+          if (cc < AT_HALF / 16 - 1) tc_ld_wait();
           tc_st16(tmem_S + lane_addr + cc * 16, cur);
         }
       }
-      // ---- the softmax reference of some row in this warp moved: rescale its O accumulator in TMEM
-      // (rare: the first tile has nothing to rescale, later tiles keep the reference unless the
-      //  overflow bound trips)
-      if (g > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
+      // ---- the softmax reference of some row moved: the half-0 warp rescales the row's O accumulator
+      // in TMEM (rare: the first tile has nothing to rescale, later tiles keep the reference unless
+      // the overflow bound trips)
+      if (hf == 0 && g > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
         mbar_wait(b_odone, (uint32_t)((g - 1) & 1));   // P·V of every earlier tile has retired
         tc_fence_after();
 #pragma unroll
@@ -401,26 +416,30 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(AttnParams p, co
       m_run = m_new;
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(b_pready(buf));   // this warp's 32 rows of P (and rescaled O) are in TMEM
+      if (lane == 0) mbar_arrive(b_pready(buf));   // this warp's share of P (and rescaled O) is in TMEM
     }
-    // ---- epilogue: O / l -> global
-    mbar_wait(b_odone, (uint32_t)((nkt - 1) & 1));
-    tc_fence_after();
-    {
+    // ---- epilogue: half-1 hands its partial denominator to half-0, which writes O / l
+    if (hf == 1) xch[128 * 3 + row] = l_run;
+    named_bar_sync(3 + qq, 64);
+    if (hf == 0) {
+      const float l_tot = l_run + xch[128 * 3 + row];
+      mbar_wait(b_odone, (uint32_t)((nkt - 1) & 1));
+      tc_fence_after();
       uint32_t o0[8], o1[8], o2[8];
       tc_ld8(tmem_O + lane_addr + 0, o0);
       tc_ld8(tmem_O + lane_addr + 8, o1);
       tc_ld8(tmem_O + lane_addr + 16, o2);
       tc_ld_wait();
-      if (qok) {
-        const float inv = 1.0f / l_run;
+      if (qok2) {
+        const long long tq2 = seq_token(sm, s, e2);
+        const float inv = 1.0f / l_tot;
         float acc[kHD];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           acc[i] = __uint_as_float(o0[i]) * inv; acc[8 + i] = __uint_as_float(o1[i]) * inv;
           acc[16 + i] = __uint_as_float(o2[i]) * inv;
         }
-        float4* op = reinterpret_cast<float4*>(p.out + (size_t)tq * kC + h * kHD);
+        float4* op = reinterpret_cast<float4*>(p.out + (size_t)tq2 * kC + h * kHD);
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
           float4 o = make_float4(acc[4*i], acc[4*i+1], acc[4*i+2], acc[4*i+3]);
@@ -428,8 +447,8 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(AttnParams p, co
           op[i] = o;
         }
       }
+      tc_fence_before();
     }
-    tc_fence_before();
   }
   tc_fence_before();
   __syncthreads();

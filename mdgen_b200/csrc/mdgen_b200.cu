@@ -364,7 +364,10 @@ int attention(mdgen_handle* h, cudaStream_t s, const float* qkv, const float* ma
     return MDGEN_OK;
   }
 #endif
-  if (sm.S <= 64) {
+  if (sm.S == 4) {
+    long long threads = sm.num_seq * 2 * 32;
+    attn_l4_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(p);
+  } else if (sm.S <= 64) {
     long long total = sm.num_seq * sm.S * kH;
     attn_small_kernel<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(p);
   } else {
