@@ -37,8 +37,8 @@ struct AttnParams {
   const float* bias_v;  // [384]
   const float* cosT;    // [>= S+1, 12]
   const float* sinT;
-  float* out;           // [N, 384]
-  int round_out;
+  void* out;            // [N, 384] fp32, or bf16 when round_out == 3
+  int round_out;        // operand rounding / storage mode of the output (see store_operand4)
   SeqMap sm;
 };
 
@@ -101,13 +101,10 @@ __global__ void __launch_bounds__(128) attn_small_kernel(AttnParams p) {
     m = mn;
   }
   float inv = 1.0f / l;
-  float4* op = reinterpret_cast<float4*>(p.out + (size_t)tq * kC + h * kHD);
 #pragma unroll
-  for (int i = 0; i < 6; ++i) {
-    float4 o = make_float4(acc[4*i] * inv, acc[4*i+1] * inv, acc[4*i+2] * inv, acc[4*i+3] * inv);
-    if (p.round_out) { o.x = round_tf32_fast(o.x); o.y = round_tf32_fast(o.y); o.z = round_tf32_fast(o.z); o.w = round_tf32_fast(o.w); }
-    op[i] = o;
-  }
+  for (int i = 0; i < 6; ++i)
+    store_operand4(p.out, (size_t)tq * kC + h * kHD + 4 * i,
+                   make_float4(acc[4*i] * inv, acc[4*i+1] * inv, acc[4*i+2] * inv, acc[4*i+3] * inv), p.round_out);
 }
 
 // ---- S == 4 (tetrapeptide residue attention, mha_l at crop 4): every q/k/v row is loaded from HBM
@@ -170,13 +167,10 @@ __global__ void __launch_bounds__(256) attn_l4_kernel(AttnParams p) {
   for (int j = 0; j < 4; ++j)
 #pragma unroll
     for (int i = 0; i < kHD; ++i) o[i] = fmaf(sc[j], __shfl_sync(0xffffffffu, v[i], j * 8 + (lane & 7)), o[i]);
-  float4* op = reinterpret_cast<float4*>(p.out + (size_t)tok * kC + h * kHD);
 #pragma unroll
-  for (int i = 0; i < 6; ++i) {
-    float4 r = make_float4(o[4*i] * inv, o[4*i+1] * inv, o[4*i+2] * inv, o[4*i+3] * inv);
-    if (p.round_out) { r.x = round_tf32_fast(r.x); r.y = round_tf32_fast(r.y); r.z = round_tf32_fast(r.z); r.w = round_tf32_fast(r.w); }
-    op[i] = r;
-  }
+  for (int i = 0; i < 6; ++i)
+    store_operand4(p.out, (size_t)tok * kC + h * kHD + 4 * i,
+                   make_float4(o[4*i] * inv, o[4*i+1] * inv, o[4*i+2] * inv, o[4*i+3] * inv), p.round_out);
 }
 
 // ---- long sequences: block = (query tile of 256, head, sequence); 128 threads x 2 queries each;
@@ -305,13 +299,11 @@ __global__ void __launch_bounds__(128) attn_flash_simt_kernel(AttnParams p) {
   for (int u = 0; u < 2; ++u) {
     if (!qok[u]) continue;
     float inv = 1.0f / l[u];
-    float4* op = reinterpret_cast<float4*>(p.out + (size_t)tq[u] * kC + h * kHD);
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      float4 o = make_float4(acc[u][4*i] * inv, acc[u][4*i+1] * inv, acc[u][4*i+2] * inv, acc[u][4*i+3] * inv);
-      if (p.round_out) { o.x = round_tf32_fast(o.x); o.y = round_tf32_fast(o.y); o.z = round_tf32_fast(o.z); o.w = round_tf32_fast(o.w); }
-      op[i] = o;
-    }
+    for (int i = 0; i < 6; ++i)
+      store_operand4(p.out, (size_t)tq[u] * kC + h * kHD + 4 * i,
+                     make_float4(acc[u][4*i] * inv, acc[u][4*i+1] * inv, acc[u][4*i+2] * inv, acc[u][4*i+3] * inv),
+                     p.round_out);
   }
 }
 

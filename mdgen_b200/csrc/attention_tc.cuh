@@ -439,13 +439,10 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(AttnParams p, co
           acc[i] = __uint_as_float(o0[i]) * inv; acc[8 + i] = __uint_as_float(o1[i]) * inv;
           acc[16 + i] = __uint_as_float(o2[i]) * inv;
         }
-        float4* op = reinterpret_cast<float4*>(p.out + (size_t)tq2 * kC + h * kHD);
 #pragma unroll
-        for (int i = 0; i < 6; ++i) {
-          float4 o = make_float4(acc[4*i], acc[4*i+1], acc[4*i+2], acc[4*i+3]);
-          if (p.round_out) { o.x = round_tf32_fast(o.x); o.y = round_tf32_fast(o.y); o.z = round_tf32_fast(o.z); o.w = round_tf32_fast(o.w); }
-          op[i] = o;
-        }
+        for (int i = 0; i < 6; ++i)
+          store_operand4(p.out, (size_t)tq2 * kC + h * kHD + 4 * i,
+                         make_float4(acc[4*i], acc[4*i+1], acc[4*i+2], acc[4*i+3]), p.round_out);
       }
       tc_fence_before();
     }

@@ -60,6 +60,37 @@ __device__ __forceinline__ float round_tf32(float x) {
 // the magnitude; the MMA's truncation of the low 13 bits completes the round-to-nearest.
 __device__ __forceinline__ float round_tf32_fast(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }
 
+// bf16 round-to-nearest-even kept in an fp32 container (precision experiments: mode 2 below)
+__device__ __forceinline__ float round_bf16_rn(float x) {
+  uint32_t u = __float_as_uint(x);
+  u = (u + 0x7FFFu + ((u >> 16) & 1u)) & 0xFFFF0000u;
+  return __uint_as_float(u);
+}
+// rounding applied by producers of GEMM operands: 0 none, 1 TF32 (tensor-core path), 2 bf16 (emulation)
+__device__ __forceinline__ float round_operand(float x, int mode) {
+  return mode == 1 ? round_tf32_fast(x) : (mode == 2 ? round_bf16_rn(x) : x);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2_rn(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+// Store 4 consecutive GEMM-operand values starting at element index `idx` of `base`:
+//   mode 0/1/2: fp32 storage (unrounded / TF32-rounded / bf16-rounded-in-fp32)
+//   mode 3    : true bf16 storage (the bf16 tensor-core GEMM path), 8 bytes
+__device__ __forceinline__ void store_operand4(void* base, size_t idx, float4 v, int mode) {
+  if (mode == 3) {
+    uint2 pk;
+    pk.x = pack_bf16x2_rn(v.x, v.y);
+    pk.y = pack_bf16x2_rn(v.z, v.w);
+    *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(base) + idx) = pk;
+  } else {
+    if (mode) { v.x = round_operand(v.x, mode); v.y = round_operand(v.y, mode); v.z = round_operand(v.z, mode); v.w = round_operand(v.w, mode); }
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + idx) = v;
+  }
+}
+
 __device__ __forceinline__ float gelu_erf(float x) {  // mdgen/model/layers.py:77-84
   return x * 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
 }

@@ -48,9 +48,8 @@ __global__ void rowdot_kernel(const float* __restrict__ W, const float* __restri
 // y = LN0(x) * (1 + scale) + shift  — no-affine LayerNorm eps 1e-6 + adaLN modulate
 // (mdgen/model/layers.py:14-15; latent_model.py:375,380,457,465,479). Optionally rounds the output
 // to TF32 (it only feeds a tensor-core GEMM).
-template <bool ROUND>
-__global__ void ln_mod_kernel(const float* __restrict__ x, float* __restrict__ y, ModRef mod,
-                              int shift_off, int scale_off, long long N) {
+__global__ void ln_mod_kernel(const float* __restrict__ x, void* __restrict__ y, ModRef mod,
+                              int shift_off, int scale_off, long long N, int rmode) {
   long long tok = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (tok >= N) return;
@@ -72,7 +71,6 @@ __global__ void ln_mod_kernel(const float* __restrict__ x, float* __restrict__ y
   const float* mr = mod_row(mod, tok);
   const float4* sh = reinterpret_cast<const float4*>(mr + shift_off);
   const float4* sc = reinterpret_cast<const float4*>(mr + scale_off);
-  float4* yr = reinterpret_cast<float4*>(y + (size_t)tok * kC);
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     float4 a = sh[i * 32 + lane], b = sc[i * 32 + lane], o;
@@ -80,8 +78,7 @@ __global__ void ln_mod_kernel(const float* __restrict__ x, float* __restrict__ y
     o.y = (v[i].y - mean) * rstd * (1.0f + b.y) + a.y;
     o.z = (v[i].z - mean) * rstd * (1.0f + b.z) + a.z;
     o.w = (v[i].w - mean) * rstd * (1.0f + b.w) + a.w;
-    if (ROUND) { o.x = round_tf32_fast(o.x); o.y = round_tf32_fast(o.y); o.z = round_tf32_fast(o.z); o.w = round_tf32_fast(o.w); }
-    yr[i * 32 + lane] = o;
+    store_operand4(y, (size_t)tok * kC + (size_t)(i * 32 + lane) * 4, o, rmode);
   }
 }
 
@@ -249,8 +246,16 @@ __global__ void pack_rows_kernel(const float* __restrict__ src, float* __restric
   long long r = i / cols;
   int c = (int)(i % cols);
   float v = src[i] * scale;
-  if (do_round) v = round_tf32(v);
+  if (do_round == 1) v = round_tf32(v);
+  if (do_round == 2) v = round_bf16_rn(v);
   dst[(size_t)(dst_row0 + r) * dst_ld + c] = v;
+}
+
+// fp32 -> bf16 (round-to-nearest-even) copy: bf16 weight copies for the kind::f16 GEMM path
+__global__ void to_bf16_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  dst[i] = (uint16_t)(pack_bf16x2_rn(src[i], 0.f) & 0xFFFFu);
 }
 
 // RoPE tables for positions 0..n-1: cos/sin(pos * inv_freq[i]), i < 12

@@ -33,7 +33,7 @@ __device__ __forceinline__ float apply_epilogue(const Epilogue& ep, float acc, l
     v = ep.resid[(size_t)m * ep.ldo + n] + mr[ep.gate_off + n] * v;
   }
   if (MODE == EPI_RESID) v = ep.resid[(size_t)m * ep.ldo + n] + v;
-  if (ep.round_out) v = round_tf32_fast(v);
+  if (ep.round_out) v = round_operand(v, ep.round_out);
   return v;
 }
 

@@ -119,6 +119,26 @@ __device__ __forceinline__ uint64_t umma_desc_k128(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// same for kind::f16 with bf16 operands: a_format = b_format = 1 (BF16)
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// two floats -> packed bf16x2 (round-to-nearest-even), low half = first argument
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
 
 // erf-GELU with erf from Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7): two MUFU ops + ~10 FMA
 // instead of erff()'s branchy ~25 instructions (the fc1 epilogue is instruction-issue bound).
@@ -157,14 +177,20 @@ __device__ __forceinline__ void tc_epilogue4(const Epilogue& ep, const float* ga
     float4 r = *reinterpret_cast<const float4*>(ep.resid + (size_t)m * ep.ldo + n);
     v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
   }
-  if (ep.round_out) { v.x = round_tf32_fast(v.x); v.y = round_tf32_fast(v.y); v.z = round_tf32_fast(v.z); v.w = round_tf32_fast(v.w); }
+  if (ep.round_out) { v.x = round_operand(v.x, ep.round_out); v.y = round_operand(v.y, ep.round_out); v.z = round_operand(v.z, ep.round_out); v.w = round_operand(v.w, ep.round_out); }
   *reinterpret_cast<float4*>(ep.out + (size_t)m * ep.ldo + n) = v;
 }
 
-template <int MODE>
+// BF16IN : operands are bf16 (kind::f16 MMA, K-block = 64 elements = 128 bytes, UMMA_K = 16) instead of
+//          TF32-in-fp32 (kind::tf32, K-block = 32 elements, UMMA_K = 8). Same 128-byte swizzled rows,
+//          same descriptors and 32-byte K advance, twice the MMA rate and half the shared-memory/L2
+//          operand traffic per FLOP (which is what bounds the fp32-operand variant).
+// BF16OUT: the epilogue stores bf16 (the fc1 hidden activations, consumed only by the fc2 GEMM).
+template <int MODE, bool BF16IN, bool BF16OUT>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                          const __grid_constant__ CUtensorMap tmB, long long M,
                                                          int N, int K, Epilogue ep) {
+  constexpr int BKE = BF16IN ? 64 : 32;                   // elements per 128-byte K-block row
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t sbase = (raw + 1023u) & ~1023u;          // SWIZZLE_128B tiles need 1024-B alignment
@@ -180,7 +206,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   const int n_blocks = N / TC_BN;
   const long long m_blocks = (M + TC_BM - 1) / TC_BM;
   const long long tiles = m_blocks * n_blocks;
-  const int kblocks = K / TC_BK;
+  const int kblocks = K / BKE;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
@@ -213,8 +239,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
           mbar_wait(empty_bar(stage), phase ^ 1u);
           mbar_expect_tx(full_bar(stage), TC_STAGE_BYTES);
           const uint32_t sa = sbase + stage * TC_STAGE_BYTES;
-          tma_load_2d(sa, &tmA, full_bar(stage), kb * TC_BK, m0);
-          tma_load_2d(sa + TC_A_BYTES, &tmB, full_bar(stage), kb * TC_BK, n0);
+          tma_load_2d(sa, &tmA, full_bar(stage), kb * BKE, m0);
+          tma_load_2d(sa + TC_A_BYTES, &tmB, full_bar(stage), kb * BKE, n0);
           if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -222,7 +248,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   } else if (warp == 1) {
     if (lane == 0) {
       // ===================== MMA issuer (one thread) =====================
-      constexpr uint32_t idesc = umma_idesc_tf32(TC_BM, TC_BN);
+      constexpr uint32_t idesc = BF16IN ? umma_idesc_bf16(TC_BM, TC_BN) : umma_idesc_tf32(TC_BM, TC_BN);
       int stage = 0;
       uint32_t phase = 0;
       uint32_t it = 0;
@@ -240,8 +266,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
 #pragma unroll
           for (int k = 0; k < TC_BK / 8; ++k) {
             // advance 8 tf32 = 32 bytes along K inside the 128-byte swizzle row: +2 in 16-B units
-            tc_mma_tf32(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                        (uint32_t)((kb | k) != 0));
+            if (BF16IN)
+              tc_mma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                          (uint32_t)((kb | k) != 0));
+            else
+              tc_mma_tf32(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                          (uint32_t)((kb | k) != 0));
           }
           tc_commit(empty_bar(stage));                      // smem slot free once these MMAs retire
           if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
@@ -308,8 +338,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
               a.z = res[itr].z + g.z * a.z; a.w = res[itr].w + g.w * a.w;
             }
             if (MODE == EPI_RESID) { a.x += res[itr].x; a.y += res[itr].y; a.z += res[itr].z; a.w += res[itr].w; }
-            if (ep.round_out) { a.x = round_tf32_fast(a.x); a.y = round_tf32_fast(a.y); a.z = round_tf32_fast(a.z); a.w = round_tf32_fast(a.w); }
-            *reinterpret_cast<float4*>(ep.out + (size_t)m * ep.ldo + n) = a;
+            if (ep.round_out) { a.x = round_operand(a.x, ep.round_out); a.y = round_operand(a.y, ep.round_out); a.z = round_operand(a.z, ep.round_out); a.w = round_operand(a.w, ep.round_out); }
+            if (BF16OUT) {
+              uint2 pk;
+              pk.x = pack_bf16x2(a.x, a.y);
+              pk.y = pack_bf16x2(a.z, a.w);
+              *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(ep.out) + (size_t)m * ep.ldo + n) = pk;
+            } else {
+              *reinterpret_cast<float4*>(ep.out + (size_t)m * ep.ldo + n) = a;
+            }
           }
         }
         __syncwarp();
@@ -327,7 +364,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
 }
 
 // ---- host side -------------------------------------------------------------------------------
-inline bool tc_gemm_supported(int N, int K) { return (N % TC_BN == 0) && (K % TC_BK == 0) && K >= TC_BK; }
+inline bool tc_gemm_supported(int N, int K, bool bf16 = false) {
+  const int bk = bf16 ? 64 : TC_BK;
+  return (N % TC_BN == 0) && (K % bk == 0) && K >= bk;
+}
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -348,15 +388,16 @@ inline PFN_encodeTiled get_encode_fn(std::string* err) {
 }
 
 // 2-D fp32 row-major [rows, cols] (leading dimension ld elements), box = [box_rows, 32 cols], SWIZZLE_128B
-inline int make_tmap_2d(CUtensorMap* map, const float* ptr, long long rows, int cols, int ld, int box_rows,
-                        std::string* err) {
+inline int make_tmap_2d(CUtensorMap* map, const void* ptr, long long rows, int cols, int ld, int box_rows,
+                        bool bf16, std::string* err) {
   PFN_encodeTiled fn = get_encode_fn(err);
   if (!fn) return -2;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
-  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * (bf16 ? 2 : 4)};
+  cuuint32_t box[2] = {(cuuint32_t)(bf16 ? 64 : TC_BK), (cuuint32_t)box_rows};   // 128-byte rows either way
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+  CUresult r = fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                  const_cast<void*>(ptr), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -367,20 +408,21 @@ inline int make_tmap_2d(CUtensorMap* map, const float* ptr, long long rows, int 
 }
 
 struct TmapCacheEntry {
-  const float* ptr; long long rows; int cols, ld, box_rows;
+  const void* ptr; long long rows; int cols, ld, box_rows; bool bf16;
   CUtensorMap map;
 };
 
-inline int get_tmap(const float* ptr, long long rows, int cols, int ld, int box_rows, CUtensorMap* out,
+inline int get_tmap(const void* ptr, long long rows, int cols, int ld, int box_rows, bool bf16, CUtensorMap* out,
                     std::string* err) {
   static std::vector<TmapCacheEntry> cache;
   for (auto& e : cache)
-    if (e.ptr == ptr && e.rows == rows && e.cols == cols && e.ld == ld && e.box_rows == box_rows) {
+    if (e.ptr == ptr && e.rows == rows && e.cols == cols && e.ld == ld && e.box_rows == box_rows &&
+        e.bf16 == bf16) {
       *out = e.map;
       return 0;
     }
-  TmapCacheEntry e{ptr, rows, cols, ld, box_rows, {}};
-  int rc = make_tmap_2d(&e.map, ptr, rows, cols, ld, box_rows, err);
+  TmapCacheEntry e{ptr, rows, cols, ld, box_rows, bf16, {}};
+  int rc = make_tmap_2d(&e.map, ptr, rows, cols, ld, box_rows, bf16, err);
   if (rc) return rc;
   if (cache.size() > 4096) cache.clear();
   cache.push_back(e);
@@ -388,20 +430,20 @@ inline int get_tmap(const float* ptr, long long rows, int cols, int ld, int box_
   return 0;
 }
 
-template <int MODE>
+template <int MODE, bool BF16IN, bool BF16OUT>
 inline int tc_launch_mode(const CUtensorMap& ta, const CUtensorMap& tb, long long M, int N, int K,
                           const Epilogue& ep, cudaStream_t s, int grid, std::string* err) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         TC_SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<MODE, BF16IN, BF16OUT>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
     if (e != cudaSuccess) {
       if (err) *err = std::string("cudaFuncSetAttribute(gemm_tc): ") + cudaGetErrorString(e);
       return -2;
     }
     configured = true;
   }
-  gemm_tc_kernel<MODE><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(ta, tb, M, N, K, ep);
+  gemm_tc_kernel<MODE, BF16IN, BF16OUT><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(ta, tb, M, N, K, ep);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     if (err) *err = std::string("gemm_tc launch: ") + cudaGetErrorString(e);
@@ -410,8 +452,10 @@ inline int tc_launch_mode(const CUtensorMap& ta, const CUtensorMap& tb, long lon
   return 0;
 }
 
-inline int tc_gemm_launch(int mode, const float* A, int lda, const float* W, int ldw, long long M, int N, int K,
-                          const Epilogue& ep, cudaStream_t s, std::string* err) {
+// A / W: fp32 (TF32-rounded) or bf16 buffers according to `in_bf16`; lda / ldw / ep.ldo in elements.
+inline int tc_gemm_launch(int mode, const void* A, int lda, const void* W, int ldw, long long M, int N, int K,
+                          const Epilogue& ep, cudaStream_t s, std::string* err, bool in_bf16 = false,
+                          bool out_bf16 = false) {
   static int num_sms = 0;
   if (!num_sms) {
     int dev = 0;
@@ -419,17 +463,31 @@ inline int tc_gemm_launch(int mode, const float* A, int lda, const float* W, int
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
   CUtensorMap ta, tb;
-  if (get_tmap(A, M, K, lda, TC_BM, &ta, err)) return -2;
-  if (get_tmap(W, N, K, ldw, TC_BN, &tb, err)) return -2;
+  if (get_tmap(A, M, K, lda, TC_BM, in_bf16, &ta, err)) return -2;
+  if (get_tmap(W, N, K, ldw, TC_BN, in_bf16, &tb, err)) return -2;
   long long tiles = ((M + TC_BM - 1) / TC_BM) * (N / TC_BN);
   int grid = (int)std::min<long long>(tiles, num_sms);
-  switch (mode) {
-    case EPI_STORE: return tc_launch_mode<EPI_STORE>(ta, tb, M, N, K, ep, s, grid, err);
-    case EPI_GELU: return tc_launch_mode<EPI_GELU>(ta, tb, M, N, K, ep, s, grid, err);
-    case EPI_RESID_GATE: return tc_launch_mode<EPI_RESID_GATE>(ta, tb, M, N, K, ep, s, grid, err);
-    case EPI_RESID: return tc_launch_mode<EPI_RESID>(ta, tb, M, N, K, ep, s, grid, err);
+  if (!in_bf16) {
+    switch (mode) {
+      case EPI_STORE: return tc_launch_mode<EPI_STORE, false, false>(ta, tb, M, N, K, ep, s, grid, err);
+      case EPI_GELU: return tc_launch_mode<EPI_GELU, false, false>(ta, tb, M, N, K, ep, s, grid, err);
+      case EPI_RESID_GATE: return tc_launch_mode<EPI_RESID_GATE, false, false>(ta, tb, M, N, K, ep, s, grid, err);
+      case EPI_RESID: return tc_launch_mode<EPI_RESID, false, false>(ta, tb, M, N, K, ep, s, grid, err);
+    }
+  } else if (!out_bf16) {
+    switch (mode) {
+      case EPI_STORE: return tc_launch_mode<EPI_STORE, true, false>(ta, tb, M, N, K, ep, s, grid, err);
+      case EPI_GELU: return tc_launch_mode<EPI_GELU, true, false>(ta, tb, M, N, K, ep, s, grid, err);
+      case EPI_RESID_GATE: return tc_launch_mode<EPI_RESID_GATE, true, false>(ta, tb, M, N, K, ep, s, grid, err);
+      case EPI_RESID: return tc_launch_mode<EPI_RESID, true, false>(ta, tb, M, N, K, ep, s, grid, err);
+    }
+  } else {
+    switch (mode) {
+      case EPI_STORE: return tc_launch_mode<EPI_STORE, true, true>(ta, tb, M, N, K, ep, s, grid, err);
+      case EPI_GELU: return tc_launch_mode<EPI_GELU, true, true>(ta, tb, M, N, K, ep, s, grid, err);
+    }
   }
-  if (err) *err = "bad epilogue mode";
+  if (err) *err = "bad epilogue mode / dtype combination";
   return -1;
 }
 

@@ -37,6 +37,8 @@ struct RawTensor {
 struct MhaW {
   float *wqkv, *bqkv, *wo, *bo, *bias_k, *bias_v;
   float *wqkv_tc, *wo_tc;
+  float *wqkv_bf, *wo_bf;   // bf16-rounded fp32 copies (precision experiments only)
+  uint16_t *wqkv_b16, *wo_b16;   // true bf16 copies for the kind::f16 GEMM path
 };
 struct IpaLayerW {
   float *ln_g, *ln_b, *head_w, *wproj, *bproj, *wout, *bout, *wproj_tc, *wout_tc;
@@ -45,7 +47,8 @@ struct IpaLayerW {
 };
 struct MainLayerW {
   MhaW mha_l, mha_t;
-  float *w1, *b1, *w2, *b2, *w1_tc, *w2_tc;
+  float *w1, *b1, *w2, *b2, *w1_tc, *w2_tc, *w1_bf, *w2_bf;
+  uint16_t *w1_b16, *w2_b16;
 };
 
 struct ProfEntry {
@@ -67,6 +70,8 @@ struct mdgen_handle {
 #else
   int use_tc = 1;      // tcgen05 TF32 GEMMs for the token GEMMs (0 = fp32 SIMT validation path)
 #endif
+  int gemm_bf16 = 1;   // token GEMMs (QKV / out / fc1 / fc2) with bf16 operands (kind::f16); 0 = TF32 operands
+  int emu_bf16 = 0;    // precision experiments: bit 0 MLP, bit 1 attention projections see bf16-rounded operands
   int use_tc_attn = 1; // tcgen05 attention for sequences longer than 64 (needs use_tc)
   int tc_min_rows = 1024;   // fewer rows (the IPA key-frame trunk) stay on the exact-fp32 skinny GEMM  // below this many rows the SIMT GEMM is used (latency-bound shapes)
   int profile = 0;
@@ -207,9 +212,17 @@ int pack_new(mdgen_handle* h, cudaStream_t s, const std::string& name, long long
 }
 
 // TF32-rounded copy of an already packed fp32 matrix.
-int tc_copy(mdgen_handle* h, cudaStream_t s, const float* src, size_t n, float** dst) {
+int tc_copy(mdgen_handle* h, cudaStream_t s, const float* src, size_t n, float** dst, int mode = 1) {
   TRY(dev_alloc_t(h, dst, n));
-  pack_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src, *dst, 1, (int)n, (int)n, 0, 1.f, 1);
+  pack_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src, *dst, 1, (int)n, (int)n, 0, 1.f, mode);
+  CHECK_LAUNCH(h);
+  return MDGEN_OK;
+}
+
+// true bf16 copy of an fp32 matrix
+int b16_copy(mdgen_handle* h, cudaStream_t s, const float* src, size_t n, uint16_t** dst) {
+  TRY(dev_alloc_t(h, dst, n));
+  to_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src, *dst, (long long)n);
   CHECK_LAUNCH(h);
   return MDGEN_OK;
 }
@@ -222,11 +235,15 @@ int pack_mha(mdgen_handle* h, cudaStream_t s, const std::string& p, MhaW* w) {
   TRY(pack(h, s, p + "attn.k_proj.weight", kC, kC, w->wqkv, kC, kC, 1.f, 0));
   TRY(pack(h, s, p + "attn.v_proj.weight", kC, kC, w->wqkv, kC, 2 * kC, 1.f, 0));
   TRY(tc_copy(h, s, w->wqkv, (size_t)kQKV * kC, &w->wqkv_tc));
+  TRY(tc_copy(h, s, w->wqkv, (size_t)kQKV * kC, &w->wqkv_bf, 2));
+  TRY(b16_copy(h, s, w->wqkv, (size_t)kQKV * kC, &w->wqkv_b16));
   TRY(pack(h, s, p + "attn.q_proj.bias", 1, kC, w->bqkv, kQKV, 0, scale, 0));
   TRY(pack(h, s, p + "attn.k_proj.bias", 1, kC, w->bqkv + kC, kQKV, 0, 1.f, 0));
   TRY(pack(h, s, p + "attn.v_proj.bias", 1, kC, w->bqkv + 2 * kC, kQKV, 0, 1.f, 0));
   TRY(pack_new(h, s, p + "attn.out_proj.weight", kC, kC, &w->wo));
   TRY(tc_copy(h, s, w->wo, (size_t)kC * kC, &w->wo_tc));
+  TRY(tc_copy(h, s, w->wo, (size_t)kC * kC, &w->wo_bf, 2));
+  TRY(b16_copy(h, s, w->wo, (size_t)kC * kC, &w->wo_b16));
   TRY(pack_new(h, s, p + "attn.out_proj.bias", 1, kC, &w->bo));
   TRY(pack_new(h, s, p + "attn.bias_k", 1, kC, &w->bias_k));
   TRY(pack_new(h, s, p + "attn.bias_v", 1, kC, &w->bias_v));
@@ -296,17 +313,21 @@ int ensure_workspace(mdgen_handle* h, long long N, long long rows, int modrows) 
 }
 
 // ---- GEMM dispatch ---------------------------------------------------------------------------
+// W = fp32 master (SIMT paths), W_tc = tensor-core operand copy: TF32-rounded fp32, or true bf16 when
+// in_bf16 (then A is a bf16 buffer too); out_bf16: the epilogue stores bf16.
 int gemm(mdgen_handle* h, cudaStream_t s, int mode, const float* A, int lda, const float* W,
-         const float* W_tc, int ldw, long long M, int N, int K, const Epilogue& ep, const char* tag) {
+         const void* W_tc, int ldw, long long M, int N, int K, const Epilogue& ep, const char* tag,
+         bool in_bf16 = false, bool out_bf16 = false) {
   ProfScope ps(h, s, tag);
 #ifndef MDGEN_NO_TC
-  if (h->use_tc && W_tc && M >= h->tc_min_rows && tc_gemm_supported(N, K)) {
-    int rc = tc_gemm_launch(mode, A, lda, W_tc, ldw, M, N, K, ep, s, &h->err);
+  if (h->use_tc && W_tc && M >= h->tc_min_rows && tc_gemm_supported(N, K, in_bf16)) {
+    int rc = tc_gemm_launch(mode, A, lda, W_tc, ldw, M, N, K, ep, s, &h->err, in_bf16, out_bf16);
     if (rc != MDGEN_OK) return rc;
     h->launches++;
     return MDGEN_OK;
   }
 #endif
+  if (in_bf16 || out_bf16) { h->err = "internal: bf16 operands need the tensor-core GEMM"; return MDGEN_E_INVALID; }
   if (M <= 4096 && N % SK_BN == 0 && K % SK_BK == 0 && lda % 4 == 0 && ldw % 4 == 0) {
     dim3 g((unsigned)((M + SK_BM - 1) / SK_BM), (unsigned)(N / SK_BN));
     switch (mode) {
@@ -378,12 +399,11 @@ int attention(mdgen_handle* h, cudaStream_t s, const float* qkv, const float* ma
   return MDGEN_OK;
 }
 
-template <bool ROUND>
 int ln_mod(mdgen_handle* h, cudaStream_t s, const float* x, float* y, const ModRef& mod, int shift_off,
-           int scale_off, long long N) {
+           int scale_off, long long N, int rmode) {
   ProfScope ps(h, s, "ln_mod");
   unsigned blocks = (unsigned)((N * 32 + 255) / 256);
-  ln_mod_kernel<ROUND><<<blocks, 256, 0, s>>>(x, y, mod, shift_off, scale_off, N);
+  ln_mod_kernel<<<blocks, 256, 0, s>>>(x, y, mod, shift_off, scale_off, N, rmode);
   CHECK_LAUNCH(h);
   return MDGEN_OK;
 }
@@ -471,15 +491,13 @@ int run_step(mdgen_handle* h, cudaStream_t s, const mdgen_cond* c, const float* 
       Epilogue eo = make_epi(w.bout, h->xi, kC);
       eo.resid = h->xi;
       TRY(gemm(h, s, EPI_RESID, h->cat, kIpaCat, w.wout, w.wout_tc, kIpaCat, rows, kC, kIpaCat, eo, "ipa_gemm"));
-      if (rti) TRY(ln_mod<true>(h, s, h->xi, h->xni, modi, off + 0, off + kC, rows));
-      else TRY(ln_mod<false>(h, s, h->xi, h->xni, modi, off + 0, off + kC, rows));
+      TRY(ln_mod(h, s, h->xi, h->xni, modi, off + 0, off + kC, rows, rti));
       TRY(gemm(h, s, EPI_STORE, h->xni, kC, w.mha.wqkv, w.mha.wqkv_tc, kC, rows, kQKV, kC,
                make_epi(w.mha.bqkv, h->qkvi, kQKV), "ipa_gemm"));
       TRY(attention(h, s, h->qkvi, h->fmask, w.mha, h->atti, smi, rti, "ipa_mha"));
       TRY(gemm(h, s, EPI_RESID_GATE, h->atti, kC, w.mha.wo, w.mha.wo_tc, kC, rows, kC, kC,
                make_epi_gate(w.mha.bo, h->xi, kC, modi, off + 2 * kC), "ipa_gemm"));
-      if (rti) TRY(ln_mod<true>(h, s, h->xi, h->xni, modi, off + 3 * kC, off + 4 * kC, rows));
-      else TRY(ln_mod<false>(h, s, h->xi, h->xni, modi, off + 3 * kC, off + 4 * kC, rows));
+      TRY(ln_mod(h, s, h->xi, h->xni, modi, off + 3 * kC, off + 4 * kC, rows, rti));
       TRY(gemm(h, s, EPI_GELU, h->xni, kC, w.w1, w.w1_tc, kC, rows, kFF, kC, make_epi(w.b1, h->hidi, kFF, rti), "ipa_gemm"));
       TRY(gemm(h, s, EPI_RESID_GATE, h->hidi, kFF, w.w2, w.w2_tc, kFF, rows, kC, kFF,
                make_epi_gate(w.b2, h->xi, kC, modi, off + 5 * kC), "ipa_gemm"));
@@ -503,28 +521,38 @@ int run_step(mdgen_handle* h, cudaStream_t s, const mdgen_cond* c, const float* 
   for (int i = 0; i < n; ++i) {
     const MainLayerW& w = h->layers[i];
     int off = n * 6 * kC + i * 9 * kC;
+    // GEMM operand modes of the token GEMMs: 3 = true bf16 storage + kind::f16 MMA (default),
+    // 1 = TF32-rounded fp32 + kind::tf32 MMA, 2 = bf16-rounded values through the TF32 MMA (precision
+    // experiments, option "emu_bf16": bit 0 MLP, bit 1 attention projections), 0 = fp32 SIMT path.
+    const bool bf = rt && h->gemm_bf16 && tc_gemm_supported(kQKV, kC, true);
+    const int rm_attn = !rt ? 0 : (bf ? 3 : ((h->emu_bf16 & 2) ? 2 : 1));
+    const int rm_mlp = !rt ? 0 : (bf ? 3 : ((h->emu_bf16 & 1) ? 2 : 1));
+    const void* wqkv_l = bf ? (const void*)w.mha_l.wqkv_b16 : ((h->emu_bf16 & 2) ? w.mha_l.wqkv_bf : w.mha_l.wqkv_tc);
+    const void* wo_l = bf ? (const void*)w.mha_l.wo_b16 : ((h->emu_bf16 & 2) ? w.mha_l.wo_bf : w.mha_l.wo_tc);
+    const void* wqkv_t = bf ? (const void*)w.mha_t.wqkv_b16 : ((h->emu_bf16 & 2) ? w.mha_t.wqkv_bf : w.mha_t.wqkv_tc);
+    const void* wo_t = bf ? (const void*)w.mha_t.wo_b16 : ((h->emu_bf16 & 2) ? w.mha_t.wo_bf : w.mha_t.wo_tc);
+    const void* w1x = bf ? (const void*)w.w1_b16 : ((h->emu_bf16 & 1) ? w.w1_bf : w.w1_tc);
+    const void* w2x = bf ? (const void*)w.w2_b16 : ((h->emu_bf16 & 1) ? w.w2_bf : w.w2_tc);
     // residue attention (over L)
-    if (rt) TRY(ln_mod<true>(h, s, h->h, h->xn, modm, off + 0, off + kC, N));
-    else TRY(ln_mod<false>(h, s, h->h, h->xn, modm, off + 0, off + kC, N));
-    TRY(gemm(h, s, EPI_STORE, h->xn, kC, w.mha_l.wqkv, w.mha_l.wqkv_tc, kC, N, kQKV, kC,
-             make_epi(w.mha_l.bqkv, h->qkv, kQKV), "gemm_qkv"));
-    TRY(attention(h, s, h->qkv, c->mask, w.mha_l, h->att, sml, rt, "mha_l"));
-    TRY(gemm(h, s, EPI_RESID_GATE, h->att, kC, w.mha_l.wo, w.mha_l.wo_tc, kC, N, kC, kC,
-             make_epi_gate(w.mha_l.bo, h->h, kC, modm, off + 2 * kC), "gemm_out"));
+    TRY(ln_mod(h, s, h->h, h->xn, modm, off + 0, off + kC, N, rm_attn));
+    TRY(gemm(h, s, EPI_STORE, h->xn, kC, w.mha_l.wqkv, wqkv_l, kC, N, kQKV, kC,
+             make_epi(w.mha_l.bqkv, h->qkv, kQKV), "gemm_qkv", bf));
+    TRY(attention(h, s, h->qkv, c->mask, w.mha_l, h->att, sml, rm_attn, "mha_l"));
+    TRY(gemm(h, s, EPI_RESID_GATE, h->att, kC, w.mha_l.wo, wo_l, kC, N, kC, kC,
+             make_epi_gate(w.mha_l.bo, h->h, kC, modm, off + 2 * kC), "gemm_out", bf));
     // time attention (over T)
-    if (rt) TRY(ln_mod<true>(h, s, h->h, h->xn, modm, off + 3 * kC, off + 4 * kC, N));
-    else TRY(ln_mod<false>(h, s, h->h, h->xn, modm, off + 3 * kC, off + 4 * kC, N));
-    TRY(gemm(h, s, EPI_STORE, h->xn, kC, w.mha_t.wqkv, w.mha_t.wqkv_tc, kC, N, kQKV, kC,
-             make_epi(w.mha_t.bqkv, h->qkv, kQKV), "gemm_qkv"));
-    TRY(attention(h, s, h->qkv, c->mask, w.mha_t, h->att, smt, rt, "mha_t"));
-    TRY(gemm(h, s, EPI_RESID_GATE, h->att, kC, w.mha_t.wo, w.mha_t.wo_tc, kC, N, kC, kC,
-             make_epi_gate(w.mha_t.bo, h->h, kC, modm, off + 5 * kC), "gemm_out"));
-    // MLP
-    if (rt) TRY(ln_mod<true>(h, s, h->h, h->xn, modm, off + 6 * kC, off + 7 * kC, N));
-    else TRY(ln_mod<false>(h, s, h->h, h->xn, modm, off + 6 * kC, off + 7 * kC, N));
-    TRY(gemm(h, s, EPI_GELU, h->xn, kC, w.w1, w.w1_tc, kC, N, kFF, kC, make_epi(w.b1, h->hid, kFF, rt), "gemm_fc1"));
-    TRY(gemm(h, s, EPI_RESID_GATE, h->hid, kFF, w.w2, w.w2_tc, kFF, N, kC, kFF,
-             make_epi_gate(w.b2, h->h, kC, modm, off + 8 * kC), "gemm_fc2"));
+    TRY(ln_mod(h, s, h->h, h->xn, modm, off + 3 * kC, off + 4 * kC, N, rm_attn));
+    TRY(gemm(h, s, EPI_STORE, h->xn, kC, w.mha_t.wqkv, wqkv_t, kC, N, kQKV, kC,
+             make_epi(w.mha_t.bqkv, h->qkv, kQKV), "gemm_qkv", bf));
+    TRY(attention(h, s, h->qkv, c->mask, w.mha_t, h->att, smt, rm_attn, "mha_t"));
+    TRY(gemm(h, s, EPI_RESID_GATE, h->att, kC, w.mha_t.wo, wo_t, kC, N, kC, kC,
+             make_epi_gate(w.mha_t.bo, h->h, kC, modm, off + 5 * kC), "gemm_out", bf));
+    // MLP (hidden activations are bf16 in bf16 mode: written by fc1, read only by fc2)
+    TRY(ln_mod(h, s, h->h, h->xn, modm, off + 6 * kC, off + 7 * kC, N, rm_mlp));
+    TRY(gemm(h, s, EPI_GELU, h->xn, kC, w.w1, w1x, kC, N, kFF, kC, make_epi(w.b1, h->hid, kFF, bf ? 0 : rm_mlp),
+             "gemm_fc1", bf, bf));
+    TRY(gemm(h, s, EPI_RESID_GATE, h->hid, kFF, w.w2, w2x, kFF, N, kC, kFF,
+             make_epi_gate(w.b2, h->h, kC, modm, off + 8 * kC), "gemm_fc2", bf));
   }
 
   // ---------------- final layer (+ Euler update)
@@ -680,9 +708,13 @@ int mdgen_finalize_weights(mdgen_handle* h, void* stream) {
     TRY(pack_mha(h, s, p + "mha_t.", &w.mha_t));
     TRY(pack_new(h, s, p + "fc1.weight", kFF, kC, &w.w1));
     TRY(tc_copy(h, s, w.w1, (size_t)kFF * kC, &w.w1_tc));
+    TRY(tc_copy(h, s, w.w1, (size_t)kFF * kC, &w.w1_bf, 2));
+    TRY(b16_copy(h, s, w.w1, (size_t)kFF * kC, &w.w1_b16));
     TRY(pack_new(h, s, p + "fc1.bias", 1, kFF, &w.b1));
     TRY(pack_new(h, s, p + "fc2.weight", kC, kFF, &w.w2));
     TRY(tc_copy(h, s, w.w2, (size_t)kC * kFF, &w.w2_tc));
+    TRY(tc_copy(h, s, w.w2, (size_t)kC * kFF, &w.w2_bf, 2));
+    TRY(b16_copy(h, s, w.w2, (size_t)kC * kFF, &w.w2_b16));
     TRY(pack_new(h, s, p + "fc2.bias", 1, kC, &w.b2));
   }
   {
@@ -813,13 +845,19 @@ int mdgen_debug_linear(mdgen_handle* h, const float* A, const float* W, const fl
   int mode = act ? EPI_GELU : EPI_STORE;
   if (use_tc) {
 #ifndef MDGEN_NO_TC
-    if (!tc_gemm_supported(N, K)) { h->err = "shape unsupported by the tensor-core GEMM"; return MDGEN_E_INVALID; }
-    float *Ar = nullptr, *Wr = nullptr;   // TF32-rounded operand copies
+    const bool bf = use_tc == 2;          // 2: bf16 operands (kind::f16), 1: TF32 operands
+    if (!tc_gemm_supported(N, K, bf)) { h->err = "shape unsupported by the tensor-core GEMM"; return MDGEN_E_INVALID; }
+    float *Ar = nullptr, *Wr = nullptr;   // rounded operand copies (fp32 containers or bf16 arrays)
     TRY(dev_alloc_t(h, &Ar, (size_t)M * K));
     TRY(dev_alloc_t(h, &Wr, (size_t)N * K));
-    pack_rows_kernel<<<(unsigned)(((size_t)M * K + 255) / 256), 256, 0, s>>>(A, Ar, M, K, K, 0, 1.f, 1);
-    pack_rows_kernel<<<(unsigned)(((size_t)N * K + 255) / 256), 256, 0, s>>>(W, Wr, N, K, K, 0, 1.f, 1);
-    int rc = tc_gemm_launch(mode, Ar, K, Wr, K, M, N, K, ep, s, &h->err);
+    if (bf) {
+      to_bf16_kernel<<<(unsigned)(((size_t)M * K + 255) / 256), 256, 0, s>>>(A, (uint16_t*)Ar, (long long)M * K);
+      to_bf16_kernel<<<(unsigned)(((size_t)N * K + 255) / 256), 256, 0, s>>>(W, (uint16_t*)Wr, (long long)N * K);
+    } else {
+      pack_rows_kernel<<<(unsigned)(((size_t)M * K + 255) / 256), 256, 0, s>>>(A, Ar, M, K, K, 0, 1.f, 1);
+      pack_rows_kernel<<<(unsigned)(((size_t)N * K + 255) / 256), 256, 0, s>>>(W, Wr, N, K, K, 0, 1.f, 1);
+    }
+    int rc = tc_gemm_launch(mode, Ar, K, Wr, K, M, N, K, ep, s, &h->err, bf, false);
     cudaStreamSynchronize(s);
     dev_free(h, Ar);
     dev_free(h, Wr);
@@ -831,7 +869,7 @@ int mdgen_debug_linear(mdgen_handle* h, const float* A, const float* W, const fl
   }
   int save = h->use_tc;
   h->use_tc = 0;
-  int rc = gemm(h, s, mode, A, K, W, nullptr, K, M, N, K, ep, "debug");
+  int rc = gemm(h, s, mode, A, K, W, (const void*)nullptr, K, M, N, K, ep, "debug");
   h->use_tc = save;
   return rc;
 }
@@ -848,6 +886,8 @@ int mdgen_set_option(mdgen_handle* h, const char* key, int64_t value) {
     h->use_tc = (int)value;
   } else if (k == "tc_min_rows") h->tc_min_rows = (int)value;
   else if (k == "use_tc_attn") h->use_tc_attn = (int)value;
+  else if (k == "emu_bf16") h->emu_bf16 = (int)value;
+  else if (k == "gemm_bf16") h->gemm_bf16 = (int)value;
   else if (k == "profile") {
     h->profile = (int)value;
     if (!value) {
@@ -864,6 +904,7 @@ int64_t mdgen_get_option(const mdgen_handle* h, const char* key) {
   if (k == "use_tc") return h->use_tc;
   if (k == "tc_min_rows") return h->tc_min_rows;
   if (k == "use_tc_attn") return h->use_tc_attn;
+  if (k == "gemm_bf16") return h->gemm_bf16;
   if (k == "profile") return h->profile;
   if (k == "modw") return h->modw;
   return -1;

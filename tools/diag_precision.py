@@ -11,9 +11,10 @@ from mdgen_b200.wrapper import NewMDGenWrapper
 cases = sys.argv[1].split(",") if len(sys.argv) > 1 else list(CASES)
 configs = [
     dict(use_tc=0),
-    dict(use_tc=1, tc_min_rows=1, use_tc_attn=1),
-    dict(use_tc=1, tc_min_rows=100000, use_tc_attn=1),   # main GEMMs SIMT too (only attention TC)
-    dict(use_tc=1, tc_min_rows=64, use_tc_attn=0),       # IPA GEMMs SIMT (rows < 64), main TC
+    dict(use_tc=1, tc_min_rows=64),                      # production: IPA trunk fp32, token GEMMs TF32
+    dict(use_tc=1, tc_min_rows=64, emu_bf16=1),          # + MLP GEMM operands rounded to bf16
+    dict(use_tc=1, tc_min_rows=64, emu_bf16=2),          # + attention projections rounded to bf16
+    dict(use_tc=1, tc_min_rows=64, emu_bf16=3),          # both
 ]
 for name in cases:
     case, args, cfg, sd, batch, zs, g = load_case(name)
