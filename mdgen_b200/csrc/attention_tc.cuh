@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(AttnParams p, co
   // ---- stage the Q tile (softmax threads: one row each), RoPE'd, scaled by log2(e), TF32-rounded
   const int r = tid;
   const int e = qt * AT_QT + r;
-  const bool qok = (tid < 128) && e < S;
+
   long long tq = 0;
   float qnorm = 0.f;
   if (tid < 128) {

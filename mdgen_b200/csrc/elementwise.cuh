@@ -127,31 +127,39 @@ __global__ void ln_affine_kernel(const float* __restrict__ x, float* __restrict_
 //   MODE 0 (once per sampling call): cond[n,c] = b_lat[c] + pos[l,c] + Wc[c,:]·x_cond[n,:] + b_c[c]
 //                                                + E_mask[x_cond_mask[n]][c]
 //   MODE 1 (every step)            : h[n,c] = Wl[c,:]·x[n,:] + cond[n,c] + ipa[b,l,c]
-constexpr int kEmbedTok = 32;  // tokens per block
+constexpr int kEmbedTok = 128;  // tokens per block (amortises the per-thread weight-row load)
 template <int MODE>
 __global__ void __launch_bounds__(kC) embed_kernel(
     const float* __restrict__ xin, int D, const float* __restrict__ W /*[C,D]*/,
     const float* __restrict__ bias0, const float* __restrict__ bias1,
     const float* __restrict__ pos /*[crop,C] or null*/, const float* __restrict__ emask /*[2,C]*/,
     const int64_t* __restrict__ cmask, const float* __restrict__ cond /*[N,C]*/,
-    const float* __restrict__ ipa /*[B,L,C]*/, float* __restrict__ out, long long N, int T, int L) {
-  __shared__ float xs[kEmbedTok][32];
+    const float* __restrict__ ipa /*[steps][B,L,C]*/, const int* __restrict__ step_ptr, long long ipa_step_stride,
+    float* __restrict__ out, long long N, int T, int L) {
+  __shared__ __align__(16) float xs[kEmbedTok][32];
   __shared__ int ms[kEmbedTok];
   int c = threadIdx.x;
   long long n0 = (long long)blockIdx.x * kEmbedTok;
   int nt = (int)min((long long)kEmbedTok, N - n0);
+  for (int i = c; i < kEmbedTok * 32; i += kC) (&xs[0][0])[i] = 0.f;
+  __syncthreads();
   for (int i = c; i < nt * D; i += kC) xs[i / D][i % D] = xin[(size_t)n0 * D + i];
   if (MODE == 0 && c < nt) ms[c] = (int)cmask[n0 + c];
   float w[28];
 #pragma unroll
   for (int k = 0; k < 28; ++k) w[k] = (k < D) ? W[(size_t)c * D + k] : 0.f;
   float bsum = (MODE == 0) ? (bias0[c] + bias1[c]) : 0.f;
+  if (MODE == 1 && step_ptr) ipa += (size_t)(*step_ptr) * ipa_step_stride;   // trunk output of this Euler step
   __syncthreads();
   for (int i = 0; i < nt; ++i) {
     long long n = n0 + i;
     float s = 0.f;
 #pragma unroll
-    for (int k = 0; k < 28; ++k) s = fmaf(w[k], xs[i][k < D ? k : 0], s);
+    for (int k4 = 0; k4 < 7; ++k4) {     // 128-bit broadcast reads of the token's latent (w[k] = 0 for k >= D)
+      const float4 xv = *reinterpret_cast<const float4*>(&xs[i][4 * k4]);
+      s = fmaf(w[4 * k4], xv.x, s); s = fmaf(w[4 * k4 + 1], xv.y, s);
+      s = fmaf(w[4 * k4 + 2], xv.z, s); s = fmaf(w[4 * k4 + 3], xv.w, s);
+    }
     if (MODE == 0) {
       int l = (int)(n % L);
       s += bsum;

@@ -180,9 +180,10 @@ __global__ void __launch_bounds__(kC) ipa_init_kernel(
     float* __restrict__ x, float* __restrict__ frot, float* __restrict__ ftrans,
     float* __restrict__ fmask /*[rows] = mask[:,0]*/, long long BL) {
   __shared__ float o7[7];
+  // rows are stacked as [replica (Euler step)][trunk (1 or 2)][B*L]
   long long row = blockIdx.x;
   long long bl = row % BL;
-  int which = (int)(row / BL);   // 0: frames=start (x_r), 1: frames=end (x_f)
+  int which = two ? (int)((row / BL) & 1) : 0;   // 0: frames=start (x_r), 1: frames=end (x_f)
   int c = threadIdx.x;
   const float* Rme = which == 0 ? srot + bl * 9 : erot + bl * 9;
   const float* tme = which == 0 ? strans + bl * 3 : etrans + bl * 3;
@@ -207,11 +208,15 @@ __global__ void __launch_bounds__(kC) ipa_init_kernel(
   x[(size_t)row * kC + c] = v;
 }
 
-// ipa_out[b,l,:] = x_r + x_f (two trunks) or a plain copy — latent_model.py:207.
-__global__ void ipa_sum_kernel(const float* __restrict__ x, float* __restrict__ out, long long n, int two) {
+// ipa_out[rep][b,l,:] = x_r + x_f (two trunks) or a plain copy — latent_model.py:207.
+// x rows are stacked [rep][trunk][B*L]; per = B*L*C elements of one trunk.
+__global__ void ipa_sum_kernel(const float* __restrict__ x, float* __restrict__ out, long long n, long long per,
+                               int two) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  out[i] = two ? x[i] + x[i + n] : x[i];
+  long long rep = i / per, rem = i - rep * per;
+  const float* src = x + rep * per * (two ? 2 : 1) + rem;
+  out[i] = two ? src[0] + src[per] : src[0];
 }
 
 }  // namespace mdgen

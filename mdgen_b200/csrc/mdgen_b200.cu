@@ -72,6 +72,7 @@ struct mdgen_handle {
 #endif
   int gemm_bf16 = 1;   // token GEMMs (QKV / out / fc1 / fc2) with bf16 operands (kind::f16); 0 = TF32 operands
   int emu_bf16 = 0;    // precision experiments: bit 0 MLP, bit 1 attention projections see bf16-rounded operands
+  bool trunk_precomputed = false;   // set by mdgen_sample_euler while the step loop runs
   int use_tc_attn = 1; // tcgen05 attention for sequences longer than 64 (needs use_tc)
   int tc_min_rows = 1024;   // fewer rows (the IPA key-frame trunk) stay on the exact-fp32 skinny GEMM  // below this many rows the SIMT GEMM is used (latency-bound shapes)
   int profile = 0;
@@ -365,13 +366,13 @@ Epilogue make_epi_gate(const float* bias, float* x, int ldo, const ModRef& mod, 
 }
 
 int attention(mdgen_handle* h, cudaStream_t s, const float* qkv, const float* mask, const MhaW& w,
-              float* out, const SeqMap& sm, int round_out, const char* tag) {
+              float* out, const SeqMap& sm, int round_out, const char* tag, bool allow_tc = true) {
   ProfScope ps(h, s, tag);
   AttnParams p;
   p.qkv = qkv; p.mask = mask; p.bias_k = w.bias_k; p.bias_v = w.bias_v;
   p.cosT = h->cosT; p.sinT = h->sinT; p.out = out; p.round_out = round_out; p.sm = sm;
 #ifndef MDGEN_NO_TC
-  if (h->use_tc && h->use_tc_attn && sm.S > 64) {
+  if (allow_tc && h->use_tc && h->use_tc_attn && sm.S > 64) {
     size_t need = attn_tc_scratch_bytes(sm);
     if (need > h->attn_scratch_bytes) {
       if (h->attn_scratch) dev_free(h, h->attn_scratch);
@@ -445,7 +446,58 @@ int build_cond(mdgen_handle* h, cudaStream_t s, const mdgen_cond* c) {
   long long N = (long long)c->B * c->T * c->L;
   embed_kernel<0><<<(unsigned)((N + kEmbedTok - 1) / kEmbedTok), kC, 0, s>>>(
       c->x_cond, h->cfg.latent_dim, h->w_cond, h->b_lat, h->b_cond, h->pos, h->e_mask, c->x_cond_mask,
-      nullptr, nullptr, h->cond, N, c->T, c->L);
+      nullptr, nullptr, nullptr, 0, h->cond, N, c->T, c->L);
+  CHECK_LAUNCH(h);
+  return MDGEN_OK;
+}
+
+// IPA key-frame trunk (latent_model.py:175-210, 369-384), exact fp32 end to end: its output is
+// broadcast-added to every frame, so TF32 rounding here is coherent over the whole trajectory (measured:
+// 40x the final-state error of TF32 in the token GEMMs). Evaluates `nrep` replicas stacked on the row
+// axis: nrep = 1 with the usual modulation-row selection (forward / per-step), or nrep = K Euler steps
+// at once (replica k uses modulation row k) — the trunk never sees x, so the sampler hoists it out of
+// the step loop.   Output: h->ipa_out [nrep][B*L][C].
+int run_ipa_trunk(mdgen_handle* h, cudaStream_t s, const mdgen_cond* c, int nrep, const int* step_ptr, int bstride) {
+  ProfScope ps(h, s, "ipa_trunk");
+  const int B = c->B, T = c->T, L = c->L, n = h->cfg.num_layers;
+  const bool two = !h->cfg.sim_condition && (h->cfg.tps_condition || h->cfg.inpainting);
+  const long long BL = (long long)B * L, rows1 = (two ? 2 : 1) * BL, rows = rows1 * nrep;
+  ModRef modi = (nrep > 1) ? ModRef{h->mod, nullptr, h->modw, 1, (int)rows1, nrep}
+                           : ModRef{h->mod, step_ptr, h->modw, bstride, L, B};
+  ipa_init_kernel<<<(unsigned)rows, kC, 0, s>>>(two ? 1 : 0, c->start_rot, c->start_trans, c->end_rot,
+                                               c->end_trans, c->aatype, h->cfg.use_aa_emb ? h->aa_emb : nullptr,
+                                               h->wf, h->bf, h->wr, h->br, c->mask, T, L, h->xi, h->frot,
+                                               h->ftrans, h->fmask, BL);
+  CHECK_LAUNCH(h);
+  SeqMap smi{L, rows / L, 1, (long long)L, 0, 1};
+  for (int i = 0; i < n; ++i) {
+    const IpaLayerW& w = h->ipa[i];
+    int off = i * 6 * kC;
+    ln_affine_kernel<false><<<(unsigned)((rows * 32 + 255) / 256), 256, 0, s>>>(h->xi, h->xni, w.ln_g, w.ln_b, rows);
+    CHECK_LAUNCH(h);
+    TRY(gemm(h, s, EPI_STORE, h->xni, kC, w.wproj, nullptr, kC, rows, kIpaProj, kC,
+             make_epi(w.bproj, h->proj, kIpaProj), "ipa_gemm"));
+    ipa_points_kernel<<<(unsigned)((rows * 96 + 255) / 256), 256, 0, s>>>(h->proj, h->frot, h->ftrans, rows);
+    CHECK_LAUNCH(h);
+    ipa_attn_kernel<<<(unsigned)rows, 128, 4 * L * sizeof(float), s>>>(h->proj, h->frot, h->ftrans, h->fmask,
+                                                                       w.head_w, h->cat, L, 0);
+    CHECK_LAUNCH(h);
+    Epilogue eo = make_epi(w.bout, h->xi, kC);
+    eo.resid = h->xi;
+    TRY(gemm(h, s, EPI_RESID, h->cat, kIpaCat, w.wout, nullptr, kIpaCat, rows, kC, kIpaCat, eo, "ipa_gemm"));
+    TRY(ln_mod(h, s, h->xi, h->xni, modi, off + 0, off + kC, rows, 0));
+    TRY(gemm(h, s, EPI_STORE, h->xni, kC, w.mha.wqkv, nullptr, kC, rows, kQKV, kC,
+             make_epi(w.mha.bqkv, h->qkvi, kQKV), "ipa_gemm"));
+    TRY(attention(h, s, h->qkvi, h->fmask, w.mha, h->atti, smi, 0, "ipa_mha", /*allow_tc=*/false));
+    TRY(gemm(h, s, EPI_RESID_GATE, h->atti, kC, w.mha.wo, nullptr, kC, rows, kC, kC,
+             make_epi_gate(w.mha.bo, h->xi, kC, modi, off + 2 * kC), "ipa_gemm"));
+    TRY(ln_mod(h, s, h->xi, h->xni, modi, off + 3 * kC, off + 4 * kC, rows, 0));
+    TRY(gemm(h, s, EPI_GELU, h->xni, kC, w.w1, nullptr, kC, rows, kFF, kC, make_epi(w.b1, h->hidi, kFF), "ipa_gemm"));
+    TRY(gemm(h, s, EPI_RESID_GATE, h->hidi, kFF, w.w2, nullptr, kFF, rows, kC, kFF,
+             make_epi_gate(w.b2, h->xi, kC, modi, off + 5 * kC), "ipa_gemm"));
+  }
+  long long ne = BL * kC * nrep;
+  ipa_sum_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, s>>>(h->xi, h->ipa_out, ne, BL * kC, two ? 1 : 0);
   CHECK_LAUNCH(h);
   return MDGEN_OK;
 }
@@ -455,63 +507,20 @@ int run_step(mdgen_handle* h, cudaStream_t s, const mdgen_cond* c, const float* 
              bool euler, const int* step_ptr, int bstride) {
   const int B = c->B, T = c->T, L = c->L, n = h->cfg.num_layers, D = h->cfg.latent_dim;
   const long long N = (long long)B * T * L;
-  const bool two = !h->cfg.sim_condition && (h->cfg.tps_condition || h->cfg.inpainting);
-  const long long BL = (long long)B * L, rows = (two ? 2 : 1) * BL;
   const int rt = (h->use_tc && N >= h->tc_min_rows) ? 1 : 0;  // round GEMM-operand activations to TF32
-  const int rti = (h->use_tc && rows >= h->tc_min_rows) ? 1 : 0;   // same, IPA-trunk GEMMs
 
-  ModRef modi{h->mod, step_ptr, h->modw, bstride, L, B};
   ModRef modm{h->mod, step_ptr, h->modw, bstride, T * L, B};
 
-  // ---------------- IPA trunk on the key frame(s)  (latent_model.py:175-210, 369-384)
-  {
-    ProfScope ps(h, s, "ipa_trunk");
-    ipa_init_kernel<<<(unsigned)rows, kC, 0, s>>>(two ? 1 : 0, c->start_rot, c->start_trans, c->end_rot,
-                                                 c->end_trans, c->aatype,
-                                                 h->cfg.use_aa_emb ? h->aa_emb : nullptr, h->wf, h->bf,
-                                                 h->wr, h->br, c->mask, T, L, h->xi, h->frot, h->ftrans,
-                                                 h->fmask, BL);
-    CHECK_LAUNCH(h);
-    SeqMap smi{L, rows / L, 1, (long long)L, 0, 1};
-    for (int i = 0; i < n; ++i) {
-      const IpaLayerW& w = h->ipa[i];
-      int off = i * 6 * kC;
-      if (rti)
-        ln_affine_kernel<true><<<(unsigned)((rows * 32 + 255) / 256), 256, 0, s>>>(h->xi, h->xni, w.ln_g, w.ln_b, rows);
-      else
-        ln_affine_kernel<false><<<(unsigned)((rows * 32 + 255) / 256), 256, 0, s>>>(h->xi, h->xni, w.ln_g, w.ln_b, rows);
-      CHECK_LAUNCH(h);
-      TRY(gemm(h, s, EPI_STORE, h->xni, kC, w.wproj, w.wproj_tc, kC, rows, kIpaProj, kC,
-               make_epi(w.bproj, h->proj, kIpaProj), "ipa_gemm"));
-      ipa_points_kernel<<<(unsigned)((rows * 96 + 255) / 256), 256, 0, s>>>(h->proj, h->frot, h->ftrans, rows);
-      CHECK_LAUNCH(h);
-      ipa_attn_kernel<<<(unsigned)rows, 128, 4 * L * sizeof(float), s>>>(h->proj, h->frot, h->ftrans, h->fmask,
-                                                                         w.head_w, h->cat, L, rti);
-      CHECK_LAUNCH(h);
-      Epilogue eo = make_epi(w.bout, h->xi, kC);
-      eo.resid = h->xi;
-      TRY(gemm(h, s, EPI_RESID, h->cat, kIpaCat, w.wout, w.wout_tc, kIpaCat, rows, kC, kIpaCat, eo, "ipa_gemm"));
-      TRY(ln_mod(h, s, h->xi, h->xni, modi, off + 0, off + kC, rows, rti));
-      TRY(gemm(h, s, EPI_STORE, h->xni, kC, w.mha.wqkv, w.mha.wqkv_tc, kC, rows, kQKV, kC,
-               make_epi(w.mha.bqkv, h->qkvi, kQKV), "ipa_gemm"));
-      TRY(attention(h, s, h->qkvi, h->fmask, w.mha, h->atti, smi, rti, "ipa_mha"));
-      TRY(gemm(h, s, EPI_RESID_GATE, h->atti, kC, w.mha.wo, w.mha.wo_tc, kC, rows, kC, kC,
-               make_epi_gate(w.mha.bo, h->xi, kC, modi, off + 2 * kC), "ipa_gemm"));
-      TRY(ln_mod(h, s, h->xi, h->xni, modi, off + 3 * kC, off + 4 * kC, rows, rti));
-      TRY(gemm(h, s, EPI_GELU, h->xni, kC, w.w1, w.w1_tc, kC, rows, kFF, kC, make_epi(w.b1, h->hidi, kFF, rti), "ipa_gemm"));
-      TRY(gemm(h, s, EPI_RESID_GATE, h->hidi, kFF, w.w2, w.w2_tc, kFF, rows, kC, kFF,
-               make_epi_gate(w.b2, h->xi, kC, modi, off + 5 * kC), "ipa_gemm"));
-    }
-    long long ne = BL * kC;
-    ipa_sum_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, s>>>(h->xi, h->ipa_out, ne, two ? 1 : 0);
-    CHECK_LAUNCH(h);
-  }
+  // ---------------- IPA trunk on the key frame(s): per step here, unless the sampler precomputed it
+  // for all steps at once (the trunk depends on t, the frames and aatype only — never on x)
+  if (!h->trunk_precomputed) TRY(run_ipa_trunk(h, s, c, 1, step_ptr, bstride));
 
   // ---------------- token embedding  (latent_model.py:233-246)
   {
     ProfScope ps(h, s, "embed");
     embed_kernel<1><<<(unsigned)((N + kEmbedTok - 1) / kEmbedTok), kC, 0, s>>>(
-        x_in, D, h->w_lat, nullptr, nullptr, nullptr, nullptr, nullptr, h->cond, h->ipa_out, h->h, N, T, L);
+        x_in, D, h->w_lat, nullptr, nullptr, nullptr, nullptr, nullptr, h->cond, h->ipa_out,
+        h->trunk_precomputed ? step_ptr : nullptr, (long long)B * L * kC, h->h, N, T, L);
     CHECK_LAUNCH(h);
   }
 
@@ -572,11 +581,11 @@ int run_step(mdgen_handle* h, cudaStream_t s, const mdgen_cond* c, const float* 
   return MDGEN_OK;
 }
 
-int prepare_call(mdgen_handle* h, cudaStream_t s, const mdgen_cond* c, int modrows) {
+int prepare_call(mdgen_handle* h, cudaStream_t s, const mdgen_cond* c, int modrows, int trunk_reps = 1) {
   TRY(check_cond(h, c));
   long long N = (long long)c->B * c->T * c->L;
   bool two = !h->cfg.sim_condition && (h->cfg.tps_condition || h->cfg.inpainting);
-  TRY(ensure_workspace(h, N, (two ? 2 : 1) * (long long)c->B * c->L, modrows));
+  TRY(ensure_workspace(h, N, (two ? 2 : 1) * (long long)c->B * c->L * trunk_reps, modrows));
   TRY(ensure_rope(h, s, std::max(c->T, c->L) + 1));
   return MDGEN_OK;
 }
@@ -771,7 +780,11 @@ int mdgen_sample_euler(mdgen_handle* h, const float* zs, const float* t_grid, in
                        const mdgen_cond* cond, float* x_out, void* stream) {
   if (!h || !zs || !t_grid || !x_out || K < 1) { if (h) h->err = "mdgen_sample_euler: bad argument"; return MDGEN_E_INVALID; }
   cudaStream_t s = (cudaStream_t)stream;
-  TRY(prepare_call(h, s, cond, K));
+  // the IPA trunk of all K steps is evaluated at once when its stacked rows stay modest
+  const bool two_t = !h->cfg.sim_condition && (h->cfg.tps_condition || h->cfg.inpainting);
+  const long long trunk_rows = (long long)K * (two_t ? 2 : 1) * cond->B * cond->L;
+  const bool hoist = trunk_rows <= 262144;
+  TRY(prepare_call(h, s, cond, K, hoist ? K : 1));
   // time rows t_k (k < K) and fp32 step sizes dt_k = t_{k+1} - t_k (integrators.py:90; torchdiffeq)
   std::vector<float> dt(K);
   for (int k = 0; k < K; ++k) dt[k] = t_grid[k + 1] - t_grid[k];
@@ -780,6 +793,8 @@ int mdgen_sample_euler(mdgen_handle* h, const float* zs, const float* t_grid, in
   CUDA_TRY(h, cudaStreamSynchronize(s));  // dt (host vector) must be consumed before it goes out of scope
   TRY(build_mod_table(h, s, K));
   TRY(build_cond(h, s, cond));
+  if (hoist) TRY(run_ipa_trunk(h, s, cond, K, nullptr, 0));
+  h->trunk_precomputed = hoist;
   step_set_kernel<<<1, 1, 0, s>>>(h->step, 0);
   CHECK_LAUNCH(h);
   // ping-pong Euler state: x_k in bufA/bufB alternately; the last step writes x_out
@@ -789,11 +804,13 @@ int mdgen_sample_euler(mdgen_handle* h, const float* zs, const float* t_grid, in
   for (int k = 0; k < K; ++k) {
     float* nxt = (k == K - 1) ? x_out : ((k & 1) == 0 ? bufA : bufB);
     if (nxt == cur) { h->err = "internal: aliasing Euler buffers"; return MDGEN_E_INVALID; }
-    TRY(run_step(h, s, cond, cur, nxt, /*euler=*/true, h->step, /*bstride=*/0));
+    int rc = run_step(h, s, cond, cur, nxt, /*euler=*/true, h->step, /*bstride=*/0);
+    if (rc != MDGEN_OK) { h->trunk_precomputed = false; return rc; }
     step_advance_kernel<<<1, 1, 0, s>>>(h->step);
     CHECK_LAUNCH(h);
     cur = nxt;
   }
+  h->trunk_precomputed = false;
   return MDGEN_OK;
 }
 
