@@ -299,18 +299,25 @@ def main():
         "gemm_qkv": 2 * N * 1152 * C, "gemm_out": 2 * N * C * C, "gemm_fc1": 2 * N * FF * C,
         "gemm_fc2": 2 * N * C * FF, "mha_t": 4 * N * H * 24 * (T + 1), "mha_l": 4 * N * H * 24 * (L + 1),
     }
-    total_ms = sum(v[0] for k, v in prof.items() if k != "ipa_trunk") or 1.0
+    total_ms = sum(v[0] for k, v in prof.items() if k != "ipa_gemm" and k != "ipa_mha") or 1.0   # (nested in ipa_trunk)
     shares = {k: round(v[0] / total_ms, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
     dom = max((k for k in prof if k in fam_flops), key=lambda k: prof[k][0])
     dom_ms = prof[dom][0] / prof[dom][1]
     achieved = fam_flops[dom] / (dom_ms / 1e3) / 1e12
     peak = peaks["bf16_tflops_sustained"]
     use_tc = eng.get_option("use_tc")
+    fam_tflops = {k: round(fam_flops[k] / (prof[k][0] / prof[k][1] / 1e3) / 1e12, 1) for k in fam_flops if k in prof}
+    # DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/r1_attention_ncu.md:
+    # attn_tc_kernel 1.53 GB read + 0.19 GB write, attn_prep_kernel 0.79 + 0.81 GB) — valid for this workload only
+    traffic = 3.32e9 if (dom == "mha_t" and (B, T, L) == (64, 1000, 4)) else None
     roofline = {
         "kernel": dom, "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-        "frac": achieved / peak, "traffic": None,
-        "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']}); the kernel uses "
-                       + ("TF32 operands whose hardware peak is half the bf16 figure"
+        "frac": achieved / peak, "traffic": traffic, "family_tflops": fam_tflops,
+        "note": "mha_t = attn_prep_kernel + attn_tc_kernel; at head_dim 24 it is bound by the MUFU ex2 pipe "
+                "(96 MMA FLOP per exponential), see profiles/r1_attention_ncu.md; the GEMM families' "
+                "achieved TFLOP/s are in family_tflops",
+        "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']}); "
+                       + ("token GEMMs: bf16 operands (kind::f16), attention: TF32 operands (half that peak)"
                           if use_tc else "fp32 SIMT FMA (validation path), not the tensor pipe"),
         "avg_launch_ms": dom_ms, "launches": prof[dom][1], "time_shares": shares,
         "whole_step_tflops": flops_forward(N, T, L) * K / (ms_per_step / 1e3) / 1e12,
@@ -329,13 +336,16 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "tf32" if use_tc else "f32", "data": "synthetic",
+            "vs_baseline": None,
+            "dtype": ("bf16" if eng.get_option("gemm_bf16") else "tf32") if use_tc else "f32", "data": "synthetic",
             "config": {"workload": f"tetrapeptide forward-sim num_frames={T} crop={L}, {K} Euler steps, "
                                    f"batch {B} per GPU (BASELINE.json configs[1])",
                        "tokens_per_forward": N, "parallelism": f"dp{world} (independent trajectories, "
                        "no data-path collective)", "l2": "working set (>4 GB activations per forward) "
                        "far exceeds the 126 MB L2; no explicit flush needed",
-                       "gemm_path": "tcgen05 TF32" if use_tc else "fp32 SIMT"},
+                       "gemm_path": ("tcgen05 " + ("bf16 operands (token GEMMs) / TF32 (attention), fp32 accumulate; "
+                                     "IPA key-frame trunk fp32" if eng.get_option("gemm_bf16") else "TF32"))
+                                    if use_tc else "fp32 SIMT"},
             "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
             "cpu_baseline": cpu_baseline,
         }
