@@ -31,7 +31,8 @@ __device__ __forceinline__ long long seq_token(const SeqMap& sm, long long s, in
 }
 
 struct AttnParams {
-  const float* qkv;     // [N, 1152]
+  const void* qkv;      // [N, 1152] fp32, or bf16 when qkv_bf16 (written by the bf16 QKV GEMM epilogue)
+  int qkv_bf16;
   const float* mask;    // [N] 1 = real token (key padding = 1 - mask), may be nullptr
   const float* bias_k;  // [384] raw (rotated at position S inside the kernel)
   const float* bias_v;  // [384]
@@ -41,6 +42,27 @@ struct AttnParams {
   int round_out;        // operand rounding / storage mode of the output (see store_operand4)
   SeqMap sm;
 };
+
+// 24 consecutive projection values (one head of q, k or v) starting at element `idx` of qkv
+__device__ __forceinline__ void load24(const void* qkv, size_t idx, int bf16, float* out) {
+  if (bf16) {
+    const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(qkv) + idx);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const uint4 u = p[i];
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        out[8 * i + 2 * j] = __uint_as_float(w[j] << 16);
+        out[8 * i + 2 * j + 1] = __uint_as_float(w[j] & 0xFFFF0000u);
+      }
+    }
+  } else {
+    const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(qkv) + idx);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { const float4 t = p[i]; out[4*i] = t.x; out[4*i+1] = t.y; out[4*i+2] = t.z; out[4*i+3] = t.w; }
+  }
+}
 
 __device__ __forceinline__ void rope24(float* x, const float* c, const float* s) {
 #pragma unroll
@@ -63,12 +85,8 @@ __global__ void __launch_bounds__(128) attn_small_kernel(AttnParams p) {
   long long s = r / sm.S;
   long long tq = seq_token(sm, s, e);
   float q[kHD], acc[kHD];
-  {
-    const float4* qp = reinterpret_cast<const float4*>(p.qkv + (size_t)tq * kQKV + h * kHD);
-#pragma unroll
-    for (int i = 0; i < 6; ++i) { float4 t = qp[i]; q[4*i] = t.x; q[4*i+1] = t.y; q[4*i+2] = t.z; q[4*i+3] = t.w; }
-    rope24(q, p.cosT + e * kHalf, p.sinT + e * kHalf);
-  }
+  load24(p.qkv, (size_t)tq * kQKV + h * kHD, p.qkv_bf16, q);
+  rope24(q, p.cosT + e * kHalf, p.sinT + e * kHalf);
 #pragma unroll
   for (int i = 0; i < kHD; ++i) acc[i] = 0.f;
   float m = -INFINITY, l = 0.f;
@@ -77,13 +95,8 @@ __global__ void __launch_bounds__(128) attn_small_kernel(AttnParams p) {
     if (j < sm.S) {
       long long tk = seq_token(sm, s, j);
       if (p.mask && p.mask[tk] == 0.f) continue;
-      const float4* kp = reinterpret_cast<const float4*>(p.qkv + (size_t)tk * kQKV + kC + h * kHD);
-      const float4* vp = reinterpret_cast<const float4*>(p.qkv + (size_t)tk * kQKV + 2 * kC + h * kHD);
-#pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        float4 t = kp[i]; k[4*i] = t.x; k[4*i+1] = t.y; k[4*i+2] = t.z; k[4*i+3] = t.w;
-        float4 u = vp[i]; v[4*i] = u.x; v[4*i+1] = u.y; v[4*i+2] = u.z; v[4*i+3] = u.w;
-      }
+      load24(p.qkv, (size_t)tk * kQKV + kC + h * kHD, p.qkv_bf16, k);
+      load24(p.qkv, (size_t)tk * kQKV + 2 * kC + h * kHD, p.qkv_bf16, v);
     } else {
 #pragma unroll
       for (int i = 0; i < kHD; ++i) { k[i] = p.bias_k[h * kHD + i]; v[i] = p.bias_v[h * kHD + i]; }
@@ -119,19 +132,11 @@ __global__ void __launch_bounds__(256) attn_l4_kernel(AttnParams p) {
   const int tl = lane >> 3, h = (int)(w & 1) * 8 + (lane & 7);
   const long long tok = seq_token(sm, s, tl);
   float q[kHD], k[kHD], v[kHD];
-  {
-    const float4* qp = reinterpret_cast<const float4*>(p.qkv + (size_t)tok * kQKV + h * kHD);
-    const float4* kp = reinterpret_cast<const float4*>(p.qkv + (size_t)tok * kQKV + kC + h * kHD);
-    const float4* vp = reinterpret_cast<const float4*>(p.qkv + (size_t)tok * kQKV + 2 * kC + h * kHD);
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      float4 a = qp[i]; q[4*i] = a.x; q[4*i+1] = a.y; q[4*i+2] = a.z; q[4*i+3] = a.w;
-      float4 b = kp[i]; k[4*i] = b.x; k[4*i+1] = b.y; k[4*i+2] = b.z; k[4*i+3] = b.w;
-      float4 c = vp[i]; v[4*i] = c.x; v[4*i+1] = c.y; v[4*i+2] = c.z; v[4*i+3] = c.w;
-    }
-    rope24(q, p.cosT + tl * kHalf, p.sinT + tl * kHalf);
-    rope24(k, p.cosT + tl * kHalf, p.sinT + tl * kHalf);
-  }
+  load24(p.qkv, (size_t)tok * kQKV + h * kHD, p.qkv_bf16, q);
+  load24(p.qkv, (size_t)tok * kQKV + kC + h * kHD, p.qkv_bf16, k);
+  load24(p.qkv, (size_t)tok * kQKV + 2 * kC + h * kHD, p.qkv_bf16, v);
+  rope24(q, p.cosT + tl * kHalf, p.sinT + tl * kHalf);
+  rope24(k, p.cosT + tl * kHalf, p.sinT + tl * kHalf);
   const float valid = (p.mask == nullptr || p.mask[tok] != 0.f) ? 1.f : 0.f;
   // scores against the 4 sibling keys + the bias key (position 4)
   float sc[5];
@@ -197,9 +202,7 @@ __global__ void __launch_bounds__(128) attn_flash_simt_kernel(AttnParams p) {
     qok[u] = e < sm.S;
     int ee = qok[u] ? e : sm.S - 1;
     tq[u] = seq_token(sm, s, ee);
-    const float4* qp = reinterpret_cast<const float4*>(p.qkv + (size_t)tq[u] * kQKV + h * kHD);
-#pragma unroll
-    for (int i = 0; i < 6; ++i) { float4 t = qp[i]; q[u][4*i] = t.x; q[u][4*i+1] = t.y; q[u][4*i+2] = t.z; q[u][4*i+3] = t.w; }
+    load24(p.qkv, (size_t)tq[u] * kQKV + h * kHD, p.qkv_bf16, q[u]);
     rope24(q[u], p.cosT + ee * kHalf, p.sinT + ee * kHalf);
 #pragma unroll
     for (int i = 0; i < kHD; ++i) { q[u][i] *= LOG2E; acc[u][i] = 0.f; }   // scores in log2 units
@@ -216,7 +219,7 @@ __global__ void __launch_bounds__(128) attn_flash_simt_kernel(AttnParams p) {
       float a = 0.f, b = 0.f;
       if (j < sm.S) {
         long long tk = seq_token(sm, s, j);
-        const float* kp = p.qkv + (size_t)tk * kQKV + kC + h * kHD;
+        const float* kp = reinterpret_cast<const float*>(p.qkv) + (size_t)tk * kQKV + kC + h * kHD;   // fp32 only
         a = kp[i]; b = kp[i + kHalf];
       } else if (j == sm.S) {
         a = p.bias_k[h * kHD + i]; b = p.bias_k[h * kHD + i + kHalf];
@@ -232,7 +235,7 @@ __global__ void __launch_bounds__(128) attn_flash_simt_kernel(AttnParams p) {
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (j < sm.S) {
         long long tk = seq_token(sm, s, j);
-        v = reinterpret_cast<const float4*>(p.qkv + (size_t)tk * kQKV + 2 * kC + h * kHD)[i];
+        v = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.qkv) + (size_t)tk * kQKV + 2 * kC + h * kHD)[i];
       } else if (j == sm.S) {
         v = reinterpret_cast<const float4*>(p.bias_v + h * kHD)[i];
       }

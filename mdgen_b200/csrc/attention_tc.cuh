@@ -158,13 +158,8 @@ __global__ void __launch_bounds__(256) attn_prep_kernel(AttnParams p, uint8_t* _
     float mval = 0.f;
     if (j < S) {
       long long tk = seq_token(sm, s, j);
-      const float4* kp = reinterpret_cast<const float4*>(p.qkv + (size_t)tk * kQKV + kC + h * kHD);
-      const float4* vp = reinterpret_cast<const float4*>(p.qkv + (size_t)tk * kQKV + 2 * kC + h * kHD);
-#pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        float4 a = kp[i]; k[4*i] = a.x; k[4*i+1] = a.y; k[4*i+2] = a.z; k[4*i+3] = a.w;
-        float4 b = vp[i]; v[4*i] = b.x; v[4*i+1] = b.y; v[4*i+2] = b.z; v[4*i+3] = b.w;
-      }
+      load24(p.qkv, (size_t)tk * kQKV + kC + h * kHD, p.qkv_bf16, k);
+      load24(p.qkv, (size_t)tk * kQKV + 2 * kC + h * kHD, p.qkv_bf16, v);
       if (p.mask && p.mask[tk] == 0.f) mval = -INFINITY;
     } else if (j == S) {
 #pragma unroll
@@ -246,9 +241,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(AttnParams p, co
   if (tid < 128) {
     tq = seq_token(sm, s, e < S ? e : S - 1);
     float q[kHD];
-    const float4* qp = reinterpret_cast<const float4*>(p.qkv + (size_t)tq * kQKV + h * kHD);
-#pragma unroll
-    for (int i = 0; i < 6; ++i) { float4 a = qp[i]; q[4*i] = a.x; q[4*i+1] = a.y; q[4*i+2] = a.z; q[4*i+3] = a.w; }
+    load24(p.qkv, (size_t)tq * kQKV + h * kHD, p.qkv_bf16, q);
     const int pe = e < S ? e : S - 1;
     rope24(q, p.cosT + pe * kHalf, p.sinT + pe * kHalf);
     float qn2 = 0.f;

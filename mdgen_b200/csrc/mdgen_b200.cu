@@ -366,10 +366,11 @@ Epilogue make_epi_gate(const float* bias, float* x, int ldo, const ModRef& mod, 
 }
 
 int attention(mdgen_handle* h, cudaStream_t s, const float* qkv, const float* mask, const MhaW& w,
-              float* out, const SeqMap& sm, int round_out, const char* tag, bool allow_tc = true) {
+              float* out, const SeqMap& sm, int round_out, const char* tag, bool allow_tc = true,
+              bool qkv_bf16 = false) {
   ProfScope ps(h, s, tag);
   AttnParams p;
-  p.qkv = qkv; p.mask = mask; p.bias_k = w.bias_k; p.bias_v = w.bias_v;
+  p.qkv = qkv; p.qkv_bf16 = qkv_bf16 ? 1 : 0; p.mask = mask; p.bias_k = w.bias_k; p.bias_v = w.bias_v;
   p.cosT = h->cosT; p.sinT = h->sinT; p.out = out; p.round_out = round_out; p.sm = sm;
 #ifndef MDGEN_NO_TC
   if (allow_tc && h->use_tc && h->use_tc_attn && sm.S > 64) {
@@ -534,6 +535,7 @@ int run_step(mdgen_handle* h, cudaStream_t s, const mdgen_cond* c, const float* 
     // 1 = TF32-rounded fp32 + kind::tf32 MMA, 2 = bf16-rounded values through the TF32 MMA (precision
     // experiments, option "emu_bf16": bit 0 MLP, bit 1 attention projections), 0 = fp32 SIMT path.
     const bool bf = rt && h->gemm_bf16 && tc_gemm_supported(kQKV, kC, true);
+    const bool bfq = bf && h->use_tc_attn;   // q|k|v stored as bf16 (the SIMT flash kernel reads fp32 only)
     const int rm_attn = !rt ? 0 : (bf ? 3 : ((h->emu_bf16 & 2) ? 2 : 1));
     const int rm_mlp = !rt ? 0 : (bf ? 3 : ((h->emu_bf16 & 1) ? 2 : 1));
     const void* wqkv_l = bf ? (const void*)w.mha_l.wqkv_b16 : ((h->emu_bf16 & 2) ? w.mha_l.wqkv_bf : w.mha_l.wqkv_tc);
@@ -545,15 +547,15 @@ int run_step(mdgen_handle* h, cudaStream_t s, const mdgen_cond* c, const float* 
     // residue attention (over L)
     TRY(ln_mod(h, s, h->h, h->xn, modm, off + 0, off + kC, N, rm_attn));
     TRY(gemm(h, s, EPI_STORE, h->xn, kC, w.mha_l.wqkv, wqkv_l, kC, N, kQKV, kC,
-             make_epi(w.mha_l.bqkv, h->qkv, kQKV), "gemm_qkv", bf));
-    TRY(attention(h, s, h->qkv, c->mask, w.mha_l, h->att, sml, rm_attn, "mha_l"));
+             make_epi(w.mha_l.bqkv, h->qkv, kQKV, (h->emu_bf16 & 4) ? 2 : 0), "gemm_qkv", bf, bfq));
+    TRY(attention(h, s, h->qkv, c->mask, w.mha_l, h->att, sml, rm_attn, "mha_l", true, bfq));
     TRY(gemm(h, s, EPI_RESID_GATE, h->att, kC, w.mha_l.wo, wo_l, kC, N, kC, kC,
              make_epi_gate(w.mha_l.bo, h->h, kC, modm, off + 2 * kC), "gemm_out", bf));
     // time attention (over T)
     TRY(ln_mod(h, s, h->h, h->xn, modm, off + 3 * kC, off + 4 * kC, N, rm_attn));
     TRY(gemm(h, s, EPI_STORE, h->xn, kC, w.mha_t.wqkv, wqkv_t, kC, N, kQKV, kC,
-             make_epi(w.mha_t.bqkv, h->qkv, kQKV), "gemm_qkv", bf));
-    TRY(attention(h, s, h->qkv, c->mask, w.mha_t, h->att, smt, rm_attn, "mha_t"));
+             make_epi(w.mha_t.bqkv, h->qkv, kQKV, (h->emu_bf16 & 4) ? 2 : 0), "gemm_qkv", bf, bfq));
+    TRY(attention(h, s, h->qkv, c->mask, w.mha_t, h->att, smt, rm_attn, "mha_t", true, bfq));
     TRY(gemm(h, s, EPI_RESID_GATE, h->att, kC, w.mha_t.wo, wo_t, kC, N, kC, kC,
              make_epi_gate(w.mha_t.bo, h->h, kC, modm, off + 5 * kC), "gemm_out", bf));
     // MLP (hidden activations are bf16 in bf16 mode: written by fc1, read only by fc2)

@@ -10,11 +10,9 @@ from mdgen_b200.wrapper import NewMDGenWrapper
 
 cases = sys.argv[1].split(",") if len(sys.argv) > 1 else list(CASES)
 configs = [
-    dict(use_tc=0),
-    dict(use_tc=1, tc_min_rows=64),                      # production: IPA trunk fp32, token GEMMs TF32
-    dict(use_tc=1, tc_min_rows=64, emu_bf16=1),          # + MLP GEMM operands rounded to bf16
-    dict(use_tc=1, tc_min_rows=64, emu_bf16=2),          # + attention projections rounded to bf16
-    dict(use_tc=1, tc_min_rows=64, emu_bf16=3),          # both
+    dict(use_tc=1, tc_min_rows=65, gemm_bf16=0),                 # TF32 token GEMMs
+    dict(use_tc=1, tc_min_rows=65, gemm_bf16=1),                 # production: bf16 token GEMMs
+    dict(use_tc=1, tc_min_rows=65, gemm_bf16=1, emu_bf16=4),     # + q,k,v rounded to bf16 (emulated)
 ]
 for name in cases:
     case, args, cfg, sd, batch, zs, g = load_case(name)
