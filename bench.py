@@ -46,6 +46,7 @@ def parse_args():
     p.add_argument("--euler-steps", type=int, default=100)
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-torch-gpu", action="store_true", help="skip timing the stock-ATen port on the GPU")
     p.add_argument("--use-tc", type=int, default=-1, help="-1 = library default")
     return p.parse_args()
 
@@ -323,6 +324,42 @@ def main():
         "whole_step_tflops": flops_forward(N, T, L) * K / (ms_per_step / 1e3) / 1e12,
     }
 
+    # ---- the north-star's denominator: the reference's stock-ATen formulation (materialised fp32
+    #      attention, no TF32) on the SAME B200, here through the pinned oracle port (it omits the
+    #      reference's wasted head-mean of the attention weights, mha.py:399-405, so it is if anything
+    #      faster than the real reference). Bounded sample: 2 of the K Euler steps, extrapolated.
+    torch_gpu = None
+    if rank == 0 and not a.no_torch_gpu:
+        try:
+            from oracle import mdgen_oracle as O
+            torch.backends.cuda.matmul.allow_tf32 = False
+            torch.backends.cudnn.allow_tf32 = False
+            sd_dev = {k_: v_.to(dev) for k_, v_ in synthetic_state_dict(m.cfg, seed=0).items()}
+            with torch.no_grad():
+                op = O.prep_batch(m.cfg, dbatch)
+                okw = dict(mask=op["mask"], start=op["start"], end=op["end"], x_cond=op["x_cond"],
+                           x_cond_mask=op["x_cond_mask"], aatype=op["aatype"])
+                ks = 2
+                g2 = grid[: ks + 1]
+                O.sample_euler(sd_dev, m.cfg, zs, grid[:2], **okw)      # warm-up (1 step)
+                torch.cuda.synchronize()
+                t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                t0.record()
+                xr = O.sample_euler(sd_dev, m.cfg, zs, g2, **okw)
+                t1.record()
+                torch.cuda.synchronize()
+                ms_ref = t0.elapsed_time(t1) / ks
+                # same-step agreement of our path with the port on this very input (sanity, not the parity gate)
+                xo = m.model.sample_euler(zs, g2, **kw)
+                agree = float((xo - xr).abs().max() / xr.abs().max())
+            torch_gpu = {"value": B * T / (ms_ref * K / 1e3), "unit": "frames/s", "ms_per_euler_step": ms_ref,
+                         "sample": f"oracle port (stock ATen, fp32, allow_tf32=False) on this B200: B={B}, "
+                                   f"{ks} of {K} Euler steps timed, extrapolated", "max_rel_diff_vs_ours_2_steps": agree}
+            del sd_dev, xr, xo, op, okw
+            torch.cuda.empty_cache()
+        except Exception as e:  # e.g. out of memory for the materialised score tensors
+            torch_gpu = {"unavailable": repr(e)[:200]}
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         threads = best_cpu_threads(T, L)
@@ -347,7 +384,7 @@ def main():
                                      "IPA key-frame trunk fp32" if eng.get_option("gemm_bf16") else "TF32"))
                                     if use_tc else "fp32 SIMT"},
             "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
-            "cpu_baseline": cpu_baseline,
+            "cpu_baseline": cpu_baseline, "torch_gpu_reference": torch_gpu,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

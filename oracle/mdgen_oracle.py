@@ -3,7 +3,9 @@
 Plain PyTorch fp32 on the host, functional over a state dict (keys of
 `LatentMDGenModel.state_dict()`), one function per reference routine with its file:line.
 It materialises the attention scores exactly like the reference does, so it is also the
-honest "port" CPU baseline that bench.py times beside the B200 numbers.
+honest "port" CPU baseline that bench.py times beside the B200 numbers. The functions are
+device-agnostic (tensors stay on the device of their inputs), which lets bench.py also time the
+same stock-ATen formulation on the B200 (the north-star's "reference single-GPU PyTorch" figure).
 
 Pinned by tests/golden/*.npz, which were produced by running the UNMODIFIED reference
 (/root/reference, imported through oracle/ref_loader.py) on the same seeded inputs; see
@@ -112,7 +114,7 @@ def get_offsets(R0, t0, R, t):
 def timestep_embedding(t, dim=256, max_period=10000):
     """mdgen/model/layers.py:30-50."""
     half = dim // 2
-    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32) / half)
+    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32) / half).to(t.device)
     args = t[:, None].float() * freqs[None]
     return torch.cat([torch.cos(args), torch.sin(args)], -1)
 
@@ -141,7 +143,7 @@ def gelu(x):
 
 def rope_tables(n: int, inv_freq: torch.Tensor):
     """fair-esm RotaryEmbedding tables for n positions (see oracle/ref_shims/esm)."""
-    t = torch.arange(n, dtype=torch.float32)
+    t = torch.arange(n, dtype=torch.float32, device=inv_freq.device)
     freqs = torch.outer(t, inv_freq.float())
     emb = torch.cat([freqs, freqs], -1)
     return emb.cos(), emb.sin()
@@ -255,7 +257,7 @@ def run_ipa(sd, cfg, temb, mask_bl, start, end, aatype):
     B, L = mask_bl.shape
     n = cfg.num_layers
     if cfg.sim_condition:
-        x = torch.zeros(B, L, C)
+        x = torch.zeros(B, L, C, device=mask_bl.device)
         if aatype is not None and cfg.use_aa_emb:
             x = x + sd["aatype_to_emb.weight"][aatype]                                # :188
         for i in range(n):
@@ -301,8 +303,8 @@ def sample_euler(sd, cfg, zs, t_grid, **kw):
     B = zs.shape[0]
     for i in range(len(t_grid) - 1):
         t0, t1 = t_grid[i], t_grid[i + 1]
-        tv = torch.ones(B) * t0                                                       # integrators.py:99
-        x = x + (t1 - t0) * forward(sd, cfg, x, tv, **kw)
+        tv = torch.ones(B, device=zs.device) * t0.to(zs.device)                       # integrators.py:99
+        x = x + (t1 - t0).to(zs.device) * forward(sd, cfg, x, tv, **kw)
     return x
 
 
@@ -319,7 +321,7 @@ def prep_batch(cfg, batch):
     if getattr(cfg, "no_torsion", False):
         tors = torch.zeros_like(tors)
     latents = torch.cat([off, tors], -1)                                              # :327
-    cond_mask = torch.zeros(B, T, L, dtype=torch.int64)
+    cond_mask = torch.zeros(B, T, L, dtype=torch.int64, device=tr.device)
     if cfg.sim_condition:
         cond_mask[:, 0] = 1
     if cfg.tps_condition:
@@ -335,7 +337,7 @@ def prep_batch(cfg, batch):
         "end": (R[:, -1], tr[:, -1]),
         "mask": batch["mask"][:, None].expand(-1, T, -1),
         "aatype": batch["seqres"],
-        "x_cond": torch.where(cond_mask[..., None].bool(), latents, torch.zeros(())),
+        "x_cond": torch.where(cond_mask[..., None].bool(), latents, torch.zeros((), device=tr.device)),
         "x_cond_mask": cond_mask,
     }
 

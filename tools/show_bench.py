@@ -9,3 +9,4 @@ print("dominant %s achieved %.1f TFLOP/s avg %.3f ms frac %.3f | whole-step %.1f
 print("shares", r["time_shares"])
 print("clocks", d["clocks"])
 if d.get("cpu_baseline"): print("cpu", d["cpu_baseline"])
+if d.get("torch_gpu_reference"): print("torch-gpu-port", d["torch_gpu_reference"])
