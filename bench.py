@@ -336,9 +336,11 @@ def main():
             torch.backends.cudnn.allow_tf32 = False
             sd_dev = {k_: v_.to(dev) for k_, v_ in synthetic_state_dict(m.cfg, seed=0).items()}
             with torch.no_grad():
-                op = O.prep_batch(m.cfg, dbatch)
-                okw = dict(mask=op["mask"], start=op["start"], end=op["end"], x_cond=op["x_cond"],
-                           x_cond_mask=op["x_cond_mask"], aatype=op["aatype"])
+                # featurisation taken from our prep kernel (the reference's batched 4x4 eigh,
+                # rigid_utils.py:191-210, fails in cuSOLVER at 256,000 matrices on this stack)
+                okw = dict(mask=kw["mask"].float(), start=(dbatch["rots"][:, 0], dbatch["trans"][:, 0]),
+                           end=(dbatch["rots"][:, -1], dbatch["trans"][:, -1]), x_cond=kw["x_cond"],
+                           x_cond_mask=kw["x_cond_mask"], aatype=kw["aatype"])
                 ks = 2
                 g2 = grid[: ks + 1]
                 O.sample_euler(sd_dev, m.cfg, zs, grid[:2], **okw)      # warm-up (1 step)
@@ -355,7 +357,7 @@ def main():
             torch_gpu = {"value": B * T / (ms_ref * K / 1e3), "unit": "frames/s", "ms_per_euler_step": ms_ref,
                          "sample": f"oracle port (stock ATen, fp32, allow_tf32=False) on this B200: B={B}, "
                                    f"{ks} of {K} Euler steps timed, extrapolated", "max_rel_diff_vs_ours_2_steps": agree}
-            del sd_dev, xr, xo, op, okw
+            del sd_dev, xr, xo, okw
             torch.cuda.empty_cache()
         except Exception as e:  # e.g. out of memory for the materialised score tensors
             torch_gpu = {"unavailable": repr(e)[:200]}
