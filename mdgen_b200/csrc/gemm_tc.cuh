@@ -8,8 +8,8 @@
 //   * warp 1: single-thread tcgen05.mma.cta_group::1.kind::tf32 issuer, A and B from shared memory
 //     through UMMA descriptors, accumulators in TMEM (2 x 192 columns, double buffered so the
 //     epilogue of tile i overlaps the MMAs of tile i+1)
-//   * warp 2: TMEM allocator;  warps 4-11: epilogue. Each warp owns a TMEM lane quarter and half
-//     of the tile's columns: tcgen05.ld 32x32b (thread = row) -> per-warp shared-memory transpose
+//   * warp 2: TMEM allocator;  warps 4-11 (residual epilogues) / 4-15 (store, GELU): epilogue. Each warp
+//     owns a TMEM lane quarter and a 96- / 64-column slice of the tile: tcgen05.ld 32x32b (thread = row) -> per-warp shared-memory transpose
 //     -> fused bias / GELU / gate*y+residual on *row-contiguous* float4s -> fully coalesced
 //     128-bit global loads/stores (4 x 128-byte lines per warp instruction)
 // Operands are fp32 bit patterns already rounded to TF32 (round-to-nearest) by their producers
@@ -31,10 +31,13 @@ constexpr int TC_BM = 128;
 constexpr int TC_BN = 192;
 constexpr int TC_BK = 32;                       // fp32 elements per K-block (128 bytes)
 constexpr int TC_STAGES = 4;
-constexpr int TC_THREADS = 384;                 // 4 control warps + 8 epilogue warps
-constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_EPI_PITCH = 36;                // floats per staged row (144 B: conflict-free float4)
-constexpr int TC_EPI_BYTES = TC_EPI_WARPS * 32 * TC_EPI_PITCH * 4;
+// epilogue warps: 8 (two 96-column halves per TMEM lane quarter) for the residual epilogues, which
+// need ~166 registers per thread; 12 (three 64-column thirds) for the store / GELU epilogues, which
+// are instruction-issue bound and fit 128 registers
+constexpr int TC_EPI_WARPS_MAX = 12;
+constexpr int TC_EPI_BYTES = TC_EPI_WARPS_MAX * 32 * TC_EPI_PITCH * 4;
+__host__ __device__ constexpr int tc_epi_warps(int mode) { return (mode == EPI_RESID_GATE || mode == EPI_RESID) ? 8 : 12; }
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
 constexpr int TC_B_BYTES = TC_BN * TC_BK * 4;   // 24 KB
 constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
@@ -187,10 +190,12 @@ __device__ __forceinline__ void tc_epilogue4(const Epilogue& ep, const float* ga
 //          operand traffic per FLOP (which is what bounds the fp32-operand variant).
 // BF16OUT: the epilogue stores bf16 (the fc1 hidden activations, consumed only by the fc2 GEMM).
 template <int MODE, bool BF16IN, bool BF16OUT>
-__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(128 + 32 * tc_epi_warps(MODE), 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                          const __grid_constant__ CUtensorMap tmB, long long M,
                                                          int N, int K, Epilogue ep) {
   constexpr int BKE = BF16IN ? 64 : 32;                   // elements per 128-byte K-block row
+  constexpr int NEPI = tc_epi_warps(MODE);                // epilogue warps
+  constexpr int ECOLS = TC_BN / (NEPI / 4);               // columns of the tile owned by one epilogue warp
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t sbase = (raw + 1023u) & ~1023u;          // SWIZZLE_128B tiles need 1024-B alignment
@@ -214,7 +219,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), TC_EPI_WARPS); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), NEPI); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -282,7 +287,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   } else if (warp >= 4) {
     // ===================== epilogue warps (TMEM -> regs -> smem transpose -> global) =====================
     const int q = warp & 3;                                 // TMEM lane quarter of this warp
-    const int half = (warp - 4) >> 2;                       // which 96-column half of the tile
+    const int half = (warp - 4) >> 2;                       // which ECOLS-column slice of the tile
     float* stg = reinterpret_cast<float*>(sgen + TC_STAGES * TC_STAGE_BYTES + 256) + (warp - 4) * 32 * TC_EPI_PITCH;
     const int rr0 = lane >> 3, c4 = lane & 7;
     // gate rows: base of the current step's modulation row (read once), + b * bstride rows per sample
@@ -293,11 +298,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
       const uint32_t buf = it & 1u, bphase = (it >> 1) & 1u;
       const long long mbase = (tile / n_blocks) * TC_BM + q * 32;
-      const int n0 = (int)(tile % n_blocks) * TC_BN + half * (TC_BN / 2);
+      const int n0 = (int)(tile % n_blocks) * TC_BN + half * ECOLS;
+      if (MODE == EPI_RESID_GATE || MODE == EPI_RESID) {
+        // pull the residual rows of this CTA's NEXT tile into L2 now (3 x 128-byte lines per lane cover
+        // this warp's 32 rows x 96 columns), so the epilogue's residual loads two tiles from now hit L2
+        // instead of exposing DRAM latency in every 32-column chunk
+        const long long tnext = tile + gridDim.x;
+        if (tnext < tiles) {
+          const long long mn = (tnext / n_blocks) * TC_BM + q * 32 + lane;
+          const int nn = (int)(tnext % n_blocks) * TC_BN + half * ECOLS;
+          if (mn < M) {
+            const float* pr = ep.resid + (size_t)mn * ep.ldo + nn;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pr));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pr + 32));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pr + 64));
+          }
+        }
+      }
       mbar_wait(tfull_bar(buf), bphase);
       tc_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < TC_BN / 2; c0 += 32) {
+      for (int c0 = 0; c0 < ECOLS; c0 += 32) {
         // residual rows of this chunk are prefetched first (8 independent 128-bit loads per lane) so
         // their DRAM/L2 latency overlaps the TMEM load and the shared-memory transpose
         float4 res[8];
@@ -310,7 +331,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
           }
         }
         uint32_t v[32];
-        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * TC_BN + half * (TC_BN / 2) + c0, v);
+        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * TC_BN + half * ECOLS + c0, v);
         tc_ld_wait();
         // thread = row: write the 32 columns of this row into the warp's staging tile
 #pragma unroll
@@ -443,7 +464,7 @@ inline int tc_launch_mode(const CUtensorMap& ta, const CUtensorMap& tb, long lon
     }
     configured = true;
   }
-  gemm_tc_kernel<MODE, BF16IN, BF16OUT><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(ta, tb, M, N, K, ep);
+  gemm_tc_kernel<MODE, BF16IN, BF16OUT><<<grid, 128 + 32 * tc_epi_warps(MODE), TC_SMEM_BYTES, s>>>(ta, tb, M, N, K, ep);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     if (err) *err = std::string("gemm_tc launch: ") + cudaGetErrorString(e);
