@@ -94,6 +94,12 @@ int mdgen_set_residue_tables(mdgen_handle* h, const float* default_frame /*host*
                              const float* atom14_group_pos /*host*/,
                              const int32_t* atom14_to_group /*host*/,
                              const float* atom14_mask /*host*/);
+/* Tables of the rollout re-featurisation (host pointers): chi atoms as atom14 indices [21,4,4], their
+ * existence mask [21,4,4] (RESTYPE_ATOM37_MASK), chi_angles_mask [21,4], backbone N/CA/C/O mask [21,4]
+ * (mdgen/residue_constants.py:33-102,1475-1478; mdgen/geometry.py:337-358). */
+int mdgen_set_featurize_tables(mdgen_handle* h, const int32_t* chi_atom14_idx /*host*/,
+                               const float* chi_atom_mask /*host*/, const float* chi_mask /*host*/,
+                               const float* bb_mask /*host*/);
 
 /* One denoiser evaluation: out[B,T,L,D] = model.forward_inference(x, t, **cond)
  * (mdgen/model/latent_model.py:263-269 -> :212-260). `t` is a device vector [B]. */
@@ -125,6 +131,14 @@ int mdgen_prep_batch(mdgen_handle* h, int32_t B, int32_t T, int32_t L, const flo
 int mdgen_decode_atom14(mdgen_handle* h, int32_t B, int32_t T, int32_t L, const float* samples,
                         const float* start_rot, const float* start_trans, const int64_t* seqres,
                         float* atom14, void* stream);
+
+/* Rollout re-featurisation on the device == what sim_inference.py:91-96 does on the
+ * host between rollouts: frames = atom14_to_frames(atom14) (mdgen/geometry.py:218-231) and torsions =
+ * atom37_to_torsions(atom14_to_atom37(atom14, seqres), seqres) (mdgen/geometry.py:9-27, 82-202).
+ *   atom14 [B,L,14,3] (one frame), seqres [B,L]
+ *   -> rots [B,L,3,3], trans [B,L,3], torsions [B,L,7,2], torsion_mask [B,L,7] (may be NULL) */
+int mdgen_featurize_atom14(mdgen_handle* h, int32_t B, int32_t L, const float* atom14, const int64_t* seqres,
+                           float* rots, float* trans, float* torsions, float* torsion_mask, void* stream);
 
 /* Introspection for tests / bench. */
 int mdgen_abi_version(void);

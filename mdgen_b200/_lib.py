@@ -21,6 +21,7 @@ EXPORTS = [
     "mdgen_finalize_weights", "mdgen_set_residue_tables", "mdgen_forward", "mdgen_sample_euler",
     "mdgen_prep_batch", "mdgen_decode_atom14", "mdgen_abi_version", "mdgen_launch_count",
     "mdgen_set_option", "mdgen_get_option", "mdgen_profile_dump", "mdgen_debug_linear",
+    "mdgen_set_featurize_tables", "mdgen_featurize_atom14",
 ]
 
 
@@ -69,6 +70,8 @@ def load_library():
                                        C.POINTER(CCond), C.c_void_p, C.c_void_p]
     lib.mdgen_prep_batch.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 7
     lib.mdgen_decode_atom14.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 6
+    lib.mdgen_set_featurize_tables.argtypes = [C.c_void_p] + [C.c_void_p] * 4
+    lib.mdgen_featurize_atom14.argtypes = [C.c_void_p, C.c_int32, C.c_int32] + [C.c_void_p] * 7
     lib.mdgen_launch_count.restype = C.c_int64
     lib.mdgen_launch_count.argtypes = [C.c_void_p]
     lib.mdgen_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
@@ -123,6 +126,11 @@ class Engine:
                 np.ascontiguousarray(z["atom14_to_group"], np.int32),
                 np.ascontiguousarray(z["atom14_mask"], np.float32)]
         self._check(self.lib.mdgen_set_residue_tables(self.h, *[a.ctypes.data for a in arrs]))
+        farrs = [np.ascontiguousarray(z["chi_atom14_idx"], np.int32),
+                 np.ascontiguousarray(z["chi_atom_mask"], np.float32),
+                 np.ascontiguousarray(z["chi_mask"], np.float32),
+                 np.ascontiguousarray(z["bb_mask"], np.float32)]
+        self._check(self.lib.mdgen_set_featurize_tables(self.h, *[a.ctypes.data for a in farrs]))
 
     def __del__(self):
         try:
@@ -234,6 +242,21 @@ class Engine:
                                               torsions.data_ptr(), lat.data_ptr(), xc.data_ptr(),
                                               cm.data_ptr(), _stream()))
         return lat, xc, cm
+
+    def featurize_atom14(self, atom14, seqres):
+        """atom14 [B,L,14,3] (one frame), seqres [B,L] -> rots, trans, torsions, torsion_mask."""
+        B, L = seqres.shape
+        a = _f32(atom14, "atom14")
+        sq = _i64(seqres, "seqres")
+        assert a.shape == (B, L, 14, 3)
+        rots = torch.empty(B, L, 3, 3, device=a.device, dtype=torch.float32)
+        trans = torch.empty(B, L, 3, device=a.device, dtype=torch.float32)
+        tors = torch.empty(B, L, 7, 2, device=a.device, dtype=torch.float32)
+        tmask = torch.empty(B, L, 7, device=a.device, dtype=torch.float32)
+        self._check(self.lib.mdgen_featurize_atom14(self.h, B, L, a.data_ptr(), sq.data_ptr(), rots.data_ptr(),
+                                                    trans.data_ptr(), tors.data_ptr(), tmask.data_ptr(),
+                                                    _stream()))
+        return rots, trans, tors, tmask
 
     def decode_atom14(self, samples, start_rot, start_trans, seqres):
         B, T, L, D = samples.shape

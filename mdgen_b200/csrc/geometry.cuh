@@ -168,4 +168,115 @@ __global__ void decode_kernel(const float* __restrict__ samples, int D, int tors
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Rollout re-featurisation: what sim_inference.py:91-96 does on the host between
+// rollouts — atom14_to_frames (mdgen/geometry.py:218-231) and atom37_to_torsions(atom14_to_atom37(.))
+// (mdgen/geometry.py:9-27, 82-202) — as one device kernel, one thread per residue, so chained rollouts
+// never leave the GPU. Algorithmic bytes per residue: 168 B in (+ previous residue's CA, C), 104 B out.
+struct FeatTables {
+  const int* chi_idx;       // [21,4,4] atom14 index of each chi atom
+  const float* chi_amask;   // [21,4,4] atom exists (RESTYPE_ATOM37_MASK)
+  const float* chi_mask;    // [21,4]   chi defined for this residue type
+  const float* bb_mask;     // [21,4]   N, CA, C, O exist
+};
+
+// Rigid.from_3_points (mdgen/rigid_utils.py:1176-1216): Gram-Schmidt frame, columns e0|e1|e2.
+__device__ __forceinline__ void frame_from_3_points(const float* pnx, const float* org, const float* pxy, float* R) {
+  float e0[3] = {org[0] - pnx[0], org[1] - pnx[1], org[2] - pnx[2]};
+  float e1[3] = {pxy[0] - org[0], pxy[1] - org[1], pxy[2] - org[2]};
+  float d = sqrtf(e0[0] * e0[0] + e0[1] * e0[1] + e0[2] * e0[2] + 1e-8f);
+  e0[0] /= d; e0[1] /= d; e0[2] /= d;
+  float dot = e0[0] * e1[0] + e0[1] * e1[1] + e0[2] * e1[2];
+  e1[0] -= e0[0] * dot; e1[1] -= e0[1] * dot; e1[2] -= e0[2] * dot;
+  d = sqrtf(e1[0] * e1[0] + e1[1] * e1[1] + e1[2] * e1[2] + 1e-8f);
+  e1[0] /= d; e1[1] /= d; e1[2] /= d;
+  float e2[3] = {e0[1] * e1[2] - e0[2] * e1[1], e0[2] * e1[0] - e0[0] * e1[2], e0[0] * e1[1] - e0[1] * e1[0]};
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { R[i * 3 + 0] = e0[i]; R[i * 3 + 1] = e1[i]; R[i * 3 + 2] = e2[i]; }
+}
+
+// (sin, cos) of the torsion defined by 4 points a0..a3   (geometry.py:172-194)
+__device__ __forceinline__ void torsion_sincos(const float* a0, const float* a1, const float* a2, const float* a3,
+                                               float* out2) {
+  float R[9];
+  frame_from_3_points(a1, a2, a0, R);
+  const float dx = a3[0] - a2[0], dy = a3[1] - a2[1], dz = a3[2] - a2[2];
+  const float ry = R[1] * dx + R[4] * dy + R[7] * dz;     // (R^T d).y
+  const float rz = R[2] * dx + R[5] * dy + R[8] * dz;     // (R^T d).z
+  const float den = sqrtf(rz * rz + ry * ry + 1e-8f);
+  out2[0] = rz / den;
+  out2[1] = ry / den;
+}
+
+__global__ void featurize_kernel(const float* __restrict__ atom14, const int64_t* __restrict__ seqres,
+                                 FeatTables tb, float* __restrict__ rots, float* __restrict__ trans,
+                                 float* __restrict__ tors, float* __restrict__ tmask, int B, int L) {
+  long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= (long long)B * L) return;
+  const int l = (int)(n % L);
+  const int aa = (int)seqres[n];
+  const float* a = atom14 + (size_t)n * 42;
+  // frames: from_3_points(C, CA, N) composed with diag(-1, 1, -1); translation = CA
+  {
+    float R[9];
+    frame_from_3_points(a + 6, a + 3, a + 0, R);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      rots[(size_t)n * 9 + i * 3 + 0] = -R[i * 3 + 0];
+      rots[(size_t)n * 9 + i * 3 + 1] = R[i * 3 + 1];
+      rots[(size_t)n * 9 + i * 3 + 2] = -R[i * 3 + 2];
+      trans[(size_t)n * 3 + i] = a[3 + i];
+    }
+  }
+  // backbone atoms as atom37 sees them (absent atoms zeroed), previous residue padded with zeros
+  float bb[4][3], pv[3][3], bm[4], pm[3];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    bm[k] = tb.bb_mask[aa * 4 + k];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) bb[k][i] = a[k * 3 + i] * bm[k];
+  }
+  if (l > 0) {
+    const int aap = (int)seqres[n - 1];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      pm[k] = tb.bb_mask[aap * 4 + k];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) pv[k][i] = a[-42 + k * 3 + i] * pm[k];
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { pm[k] = 0.f; pv[k][0] = pv[k][1] = pv[k][2] = 0.f; }
+  }
+  float sc[7][2], m[7];
+  torsion_sincos(pv[1], pv[2], bb[0], bb[1], sc[0]);   // pre-omega: CA-, C-, N, CA
+  torsion_sincos(pv[2], bb[0], bb[1], bb[2], sc[1]);   // phi:       C-, N, CA, C
+  torsion_sincos(bb[0], bb[1], bb[2], bb[3], sc[2]);   // psi:       N, CA, C, O
+  sc[2][0] = -sc[2][0]; sc[2][1] = -sc[2][1];          // geometry.py:196-201
+  m[0] = pm[1] * pm[2] * bm[0] * bm[1];
+  m[1] = pm[2] * bm[0] * bm[1] * bm[2];
+  m[2] = bm[0] * bm[1] * bm[2] * bm[3];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    float p[4][3];
+    float am = 1.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int idx = tb.chi_idx[(aa * 4 + c) * 4 + k];
+      const float mk = tb.chi_amask[(aa * 4 + c) * 4 + k];
+      am *= mk;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) p[k][i] = a[idx * 3 + i] * mk;
+    }
+    torsion_sincos(p[0], p[1], p[2], p[3], sc[3 + c]);
+    m[3 + c] = tb.chi_mask[aa * 4 + c] * am;
+  }
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    tors[(size_t)n * 14 + 2 * k] = sc[k][0];
+    tors[(size_t)n * 14 + 2 * k + 1] = sc[k][1];
+    if (tmask) tmask[(size_t)n * 7 + k] = m[k];
+  }
+}
+
 }  // namespace mdgen

@@ -94,6 +94,8 @@ struct mdgen_handle {
   // residue tables
   float *tb_frame = nullptr, *tb_pos = nullptr, *tb_mask = nullptr;
   int* tb_group = nullptr;
+  int* ft_chi_idx = nullptr;
+  float *ft_chi_amask = nullptr, *ft_chi_mask = nullptr, *ft_bb_mask = nullptr;
 
   // workspace
   long long cap_tokens = 0, cap_rows = 0;
@@ -764,6 +766,39 @@ int mdgen_set_residue_tables(mdgen_handle* h, const float* default_frame, const 
   CUDA_TRY(h, cudaMemcpy(h->tb_pos, atom14_group_pos, 21 * 14 * 3 * 4, cudaMemcpyHostToDevice));
   CUDA_TRY(h, cudaMemcpy(h->tb_group, atom14_to_group, 21 * 14 * 4, cudaMemcpyHostToDevice));
   CUDA_TRY(h, cudaMemcpy(h->tb_mask, atom14_mask, 21 * 14 * 4, cudaMemcpyHostToDevice));
+  return MDGEN_OK;
+}
+
+int mdgen_set_featurize_tables(mdgen_handle* h, const int32_t* chi_atom14_idx, const float* chi_atom_mask,
+                               const float* chi_mask, const float* bb_mask) {
+  if (!h || !chi_atom14_idx || !chi_atom_mask || !chi_mask || !bb_mask) return MDGEN_E_INVALID;
+  if (!h->ft_chi_idx) {
+    TRY(dev_alloc_t(h, &h->ft_chi_idx, 21 * 16));
+    TRY(dev_alloc_t(h, &h->ft_chi_amask, 21 * 16));
+    TRY(dev_alloc_t(h, &h->ft_chi_mask, 21 * 4));
+    TRY(dev_alloc_t(h, &h->ft_bb_mask, 21 * 4));
+  }
+  CUDA_TRY(h, cudaMemcpy(h->ft_chi_idx, chi_atom14_idx, 21 * 16 * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(h, cudaMemcpy(h->ft_chi_amask, chi_atom_mask, 21 * 16 * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(h, cudaMemcpy(h->ft_chi_mask, chi_mask, 21 * 4 * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(h, cudaMemcpy(h->ft_bb_mask, bb_mask, 21 * 4 * 4, cudaMemcpyHostToDevice));
+  return MDGEN_OK;
+}
+
+int mdgen_featurize_atom14(mdgen_handle* h, int32_t B, int32_t L, const float* atom14, const int64_t* seqres,
+                           float* rots, float* trans, float* torsions, float* torsion_mask, void* stream) {
+  if (!h || !atom14 || !seqres || !rots || !trans || !torsions || B <= 0 || L <= 0) {
+    if (h) h->err = "mdgen_featurize_atom14: bad argument";
+    return MDGEN_E_INVALID;
+  }
+  if (!h->ft_chi_idx) { h->err = "featurisation tables not set"; return MDGEN_E_WEIGHTS; }
+  cudaStream_t s = (cudaStream_t)stream;
+  ProfScope ps(h, s, "featurize");
+  FeatTables tb{h->ft_chi_idx, h->ft_chi_amask, h->ft_chi_mask, h->ft_bb_mask};
+  long long N = (long long)B * L;
+  featurize_kernel<<<(unsigned)((N + 127) / 128), 128, 0, s>>>(atom14, seqres, tb, rots, trans, torsions,
+                                                              torsion_mask, B, L);
+  CHECK_LAUNCH(h);
   return MDGEN_OK;
 }
 

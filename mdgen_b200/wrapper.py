@@ -108,6 +108,32 @@ class NewMDGenWrapper(_Base):
         aa_out = batch["seqres"][:, None].expand(B, T, L)            # wrapper.py:483
         return atom14, aa_out
 
+    @torch.no_grad()
+    def rollout(self, batch, zs=None, num_steps=None):
+        """One forward-simulation rollout with on-device re-featurisation of its last frame ==
+        `rollout(model, batch)` of sim_inference.py:61-98 without the device->CPU->device round trip
+        (`atom14_to_frames` / `atom37_to_torsions` run in `mdgen_featurize_atom14`).
+        `batch` holds ONE conditioning frame per trajectory (T = 1); returns (atom14, new_batch) where
+        `new_batch` seeds the next rollout."""
+        T = self.args.num_frames
+        expanded = {
+            "torsions": batch["torsions"].expand(-1, T, -1, -1, -1),
+            "torsion_mask": batch["torsion_mask"],
+            "trans": batch["trans"].expand(-1, T, -1, -1),
+            "rots": batch["rots"].expand(-1, T, -1, -1, -1),
+            "seqres": batch["seqres"],
+            "mask": batch["mask"],
+        }
+        atom14, _ = self.inference(expanded, zs=zs, num_steps=num_steps)
+        eng = self.model.engine()
+        with torch.cuda.device(atom14.device):
+            rots, trans, tors, _ = eng.featurize_atom14(atom14[:, -1], batch["seqres"])
+        new_batch = dict(batch)
+        new_batch["rots"] = rots[:, None]
+        new_batch["trans"] = trans[:, None]
+        new_batch["torsions"] = tors[:, None]
+        return atom14, new_batch
+
     # -- training hooks: kept as names; the backward path is a 'next' row (SURVEY.md §8f-3) -----
     def general_step(self, batch, stage="train"):
         raise NotImplementedError("mdgen_b200: training step not implemented (SURVEY.md §8f-3)")

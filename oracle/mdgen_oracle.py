@@ -396,3 +396,52 @@ def decode_atom14(cfg, samples, R0, t0, seqres):
     tb = residue_tables()
     gR, gt = torsion_angles_to_frames(fR, ft, tors, aat, tb)
     return frames_to_atom14(gR, gt, aat, tb)
+
+
+# --------------------------------------------------------------------------- rollout re-featurisation
+def from_3_points(p_neg_x, origin, p_xy, eps=1e-8):
+    """Rigid.from_3_points — mdgen/rigid_utils.py:1176-1216 (Gram-Schmidt; columns e0,e1,e2)."""
+    e0 = origin - p_neg_x
+    e1 = p_xy - origin
+    e0 = e0 / torch.sqrt((e0 * e0).sum(-1, keepdim=True) + eps)
+    dot = (e0 * e1).sum(-1, keepdim=True)
+    e1 = e1 - e0 * dot
+    e1 = e1 / torch.sqrt((e1 * e1).sum(-1, keepdim=True) + eps)
+    e2 = torch.cross(e0, e1, dim=-1)
+    return torch.stack([e0, e1, e2], -1), origin          # R[..., i, j] = e_j[i]
+
+
+def featurize_atom14(atom14, seqres):
+    """What sim_inference.py:91-96 does between rollouts, for every batch row:
+      frames   = atom14_to_frames(atom14)                       (mdgen/geometry.py:218-231)
+      torsions = atom37_to_torsions(atom14_to_atom37(atom14))   (mdgen/geometry.py:9-27, 82-202)
+    atom14 [B,L,14,3], seqres [B,L] -> rots [B,L,3,3], trans [B,L,3], torsions [B,L,7,2], mask [B,L,7]."""
+    tb = residue_tables()
+    B, L = seqres.shape
+    # frames from (C, CA, N), then compose with diag(-1, 1, -1)   geometry.py:219-231
+    R, t = from_3_points(atom14[..., 2, :], atom14[..., 1, :], atom14[..., 0, :])
+    R = R * torch.tensor([-1.0, 1.0, -1.0])[None, None, None, :]
+    # backbone atoms as atom37 sees them (absent atoms are zeroed by RESTYPE_ATOM37_MASK)
+    bbm = tb["bb_mask"][seqres]                                     # [B,L,4]  N, CA, C, O
+    bb = atom14[..., :4, :] * bbm[..., None]
+    prev = torch.cat([torch.zeros_like(bb[:, :1]), bb[:, :-1]], 1)  # geometry.py:95-98
+    prevm = torch.cat([torch.zeros_like(bbm[:, :1]), bbm[:, :-1]], 1)
+    pre_omega = torch.stack([prev[..., 1, :], prev[..., 2, :], bb[..., 0, :], bb[..., 1, :]], -2)   # :103-106
+    phi = torch.stack([prev[..., 2, :], bb[..., 0, :], bb[..., 1, :], bb[..., 2, :]], -2)            # :107-110
+    psi = torch.stack([bb[..., 0, :], bb[..., 1, :], bb[..., 2, :], bb[..., 3, :]], -2)              # :111-114
+    pre_omega_m = prevm[..., 1] * prevm[..., 2] * bbm[..., 0] * bbm[..., 1]                          # :116-118
+    phi_m = prevm[..., 2] * bbm[..., 0] * bbm[..., 1] * bbm[..., 2]
+    psi_m = bbm[..., 0] * bbm[..., 1] * bbm[..., 2] * bbm[..., 3]
+    idx = tb["chi_atom14_idx"][seqres].long()                                                        # [B,L,4,4]
+    am = tb["chi_atom_mask"][seqres]
+    chis = torch.gather(atom14[:, :, None].expand(B, L, 4, 14, 3), 3,
+                        idx[..., None].expand(B, L, 4, 4, 3)) * am[..., None]                       # :128-133
+    chis_m = tb["chi_mask"][seqres] * am.prod(-1)                                                    # :135-150
+    pos = torch.cat([pre_omega[:, :, None], phi[:, :, None], psi[:, :, None], chis], 2)              # [B,L,7,4,3]
+    tmask = torch.cat([pre_omega_m[..., None], phi_m[..., None], psi_m[..., None], chis_m], -1)
+    fR, ft = from_3_points(pos[..., 1, :], pos[..., 2, :], pos[..., 0, :])                           # :172-177
+    rel = rot_vec_mul(fR.transpose(-1, -2), pos[..., 3, :] - ft)                                     # :179
+    sc = torch.stack([rel[..., 2], rel[..., 1]], -1)                                                 # :181-183
+    sc = sc / torch.sqrt((sc * sc).sum(-1, keepdim=True) + 1e-8)                                     # :185-194
+    sc = sc * torch.tensor([1.0, 1.0, -1.0, 1.0, 1.0, 1.0, 1.0])[None, None, :, None]                # :196-201
+    return R, t, sc, tmask

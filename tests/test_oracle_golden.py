@@ -58,3 +58,23 @@ def test_rope_shim_matches_hf_esm_port():
     cos, sin = O.rope_tables(8, Shim(24).inv_freq)
     ok = k * cos + O.rotate_half(k) * sin
     assert torch.allclose(ok, hk, atol=0, rtol=0)
+
+
+def test_featurize_oracle_matches_reference_golden(golden_dir):
+    """Rollout re-featurisation: oracle vs the reference's atom14_to_frames /
+    atom37_to_torsions outputs on the last frame of its own inference() results."""
+    import os
+
+    import numpy as np
+    from mdgen_b200.synthetic import synthetic_batch
+    f = dict(np.load(os.path.join(golden_dir, "featurize.npz")))
+    for name in ("sim_c1", "atlas_small", "tps"):
+        case = CASES[name]
+        g = np.load(os.path.join(golden_dir, f"{name}.npz"))
+        batch = synthetic_batch(case["B"], case["T"], case["L"], seed=1, **case.get("batch", {}))
+        a14 = torch.from_numpy(g["atom14"])[:, -1]
+        R, t, sc, m = O.featurize_atom14(a14, batch["seqres"])
+        assert (R - torch.from_numpy(f[f"{name}/rots"])).abs().max() < 1e-5
+        assert (t - torch.from_numpy(f[f"{name}/trans"])).abs().max() < 1e-6
+        assert (sc - torch.from_numpy(f[f"{name}/torsions"])).abs().max() < 2e-5
+        assert (m.numpy() == f[f"{name}/torsion_mask"]).all()
