@@ -806,6 +806,7 @@ int mdgen_forward(mdgen_handle* h, const float* x, const float* t, const mdgen_c
                   void* stream) {
   if (!h || !x || !t || !out) { if (h) h->err = "mdgen_forward: null argument"; return MDGEN_E_INVALID; }
   cudaStream_t s = (cudaStream_t)stream;
+  h->trunk_precomputed = false;
   TRY(prepare_call(h, s, cond, cond ? cond->B : 0));
   CUDA_TRY(h, cudaMemcpyAsync(h->tvals, t, (size_t)cond->B * sizeof(float), cudaMemcpyDeviceToDevice, s));
   TRY(build_mod_table(h, s, cond->B));
@@ -840,7 +841,7 @@ int mdgen_sample_euler(mdgen_handle* h, const float* zs, const float* t_grid, in
   float* bufB = h->xbuf2;
   for (int k = 0; k < K; ++k) {
     float* nxt = (k == K - 1) ? x_out : ((k & 1) == 0 ? bufA : bufB);
-    if (nxt == cur) { h->err = "internal: aliasing Euler buffers"; return MDGEN_E_INVALID; }
+    // (K == 1 with x_out == zs updates in place: each state element is read and written by the same thread)
     int rc = run_step(h, s, cond, cur, nxt, /*euler=*/true, h->step, /*bstride=*/0);
     if (rc != MDGEN_OK) { h->trunk_precomputed = false; return rc; }
     step_advance_kernel<<<1, 1, 0, s>>>(h->step);
