@@ -285,3 +285,27 @@ def test_featurize_atom14_matches_reference_golden(golden_dir):
     assert (nb["rots"][:, 0].cpu() - Ro).abs().max() < 1e-5 and (nb["torsions"][:, 0].cpu() - so).abs().max() < 5e-5
     a2, _ = m.rollout(nb, zs=zs.cuda(), num_steps=4)
     assert torch.isfinite(a2).all() and a2.shape == a1.shape
+
+
+def test_atlas_shape_forward_matches_oracle():
+    """ATLAS-shaped chain (crop 256, no abs_pos_emb, 16 padded residues): residue attention over
+    L = 256 runs on the tcgen05 attention kernel, the IPA trunk sees 256 residues per sample."""
+    from mdgen_b200.config import config_from_args, default_args
+    from oracle import mdgen_oracle as O
+    B, T, L = 1, 66, 256
+    args = default_args(sim_condition=True, prepend_ipa=True, crop=L, num_frames=T, sampling_method="euler")
+    cfg = config_from_args(args)
+    sd = synthetic_state_dict(cfg, seed=0)
+    batch = synthetic_batch(B, T, L, seed=9, pad_last=16)
+    zs = synthetic_noise(B, T, L, cfg.latent_dim, seed=10)
+    m = _wrapper(args, sd, "bf16")
+    kw = m.prep_batch(_dev(batch))["model_kwargs"]
+    t = torch.tensor([0.35])
+    v = m.model.forward_inference(zs.cuda(), t.cuda(), **kw)
+    op = O.prep_batch(cfg, batch)
+    okw = dict(mask=op["mask"], start=op["start"], end=op["end"], x_cond=op["x_cond"],
+               x_cond_mask=op["x_cond_mask"], aatype=op["aatype"])
+    with torch.no_grad():
+        vo = O.forward(sd, cfg, zs, t, **okw)
+    assert max_rel(v.cpu(), vo) < TOL, max_rel(v.cpu(), vo)
+    assert rel_l2(v.cpu(), vo) < TOL
