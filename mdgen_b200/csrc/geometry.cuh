@@ -181,31 +181,47 @@ struct FeatTables {
 };
 
 // Rigid.from_3_points (mdgen/rigid_utils.py:1176-1216): Gram-Schmidt frame, columns e0|e1|e2.
+// Written with explicit round-to-nearest intrinsics in the reference's exact operation order (no FMA
+// contraction): several torsions of the reference are *degenerate* (first residue's pre-omega / phi
+// use zero-padded atoms, undefined chis use four identical atoms), where the result is decided by
+// rounding, so only an identical operation sequence reproduces the reference's values.
+__device__ __forceinline__ float sumsq3(const float* v) {
+  return __fadd_rn(__fadd_rn(__fmul_rn(v[0], v[0]), __fmul_rn(v[1], v[1])), __fmul_rn(v[2], v[2]));
+}
+__device__ __forceinline__ float dot3(const float* a, const float* b) {
+  return __fadd_rn(__fadd_rn(__fmul_rn(a[0], b[0]), __fmul_rn(a[1], b[1])), __fmul_rn(a[2], b[2]));
+}
 __device__ __forceinline__ void frame_from_3_points(const float* pnx, const float* org, const float* pxy, float* R) {
-  float e0[3] = {org[0] - pnx[0], org[1] - pnx[1], org[2] - pnx[2]};
-  float e1[3] = {pxy[0] - org[0], pxy[1] - org[1], pxy[2] - org[2]};
-  float d = sqrtf(e0[0] * e0[0] + e0[1] * e0[1] + e0[2] * e0[2] + 1e-8f);
-  e0[0] /= d; e0[1] /= d; e0[2] /= d;
-  float dot = e0[0] * e1[0] + e0[1] * e1[1] + e0[2] * e1[2];
-  e1[0] -= e0[0] * dot; e1[1] -= e0[1] * dot; e1[2] -= e0[2] * dot;
-  d = sqrtf(e1[0] * e1[0] + e1[1] * e1[1] + e1[2] * e1[2] + 1e-8f);
-  e1[0] /= d; e1[1] /= d; e1[2] /= d;
-  float e2[3] = {e0[1] * e1[2] - e0[2] * e1[1], e0[2] * e1[0] - e0[0] * e1[2], e0[0] * e1[1] - e0[1] * e1[0]};
+  float e0[3] = {__fsub_rn(org[0], pnx[0]), __fsub_rn(org[1], pnx[1]), __fsub_rn(org[2], pnx[2])};
+  float e1[3] = {__fsub_rn(pxy[0], org[0]), __fsub_rn(pxy[1], org[1]), __fsub_rn(pxy[2], org[2])};
+  float d = __fsqrt_rn(__fadd_rn(sumsq3(e0), 1e-8f));
+  e0[0] = __fdiv_rn(e0[0], d); e0[1] = __fdiv_rn(e0[1], d); e0[2] = __fdiv_rn(e0[2], d);
+  const float dot = dot3(e0, e1);
+  e1[0] = __fsub_rn(e1[0], __fmul_rn(e0[0], dot));
+  e1[1] = __fsub_rn(e1[1], __fmul_rn(e0[1], dot));
+  e1[2] = __fsub_rn(e1[2], __fmul_rn(e0[2], dot));
+  d = __fsqrt_rn(__fadd_rn(sumsq3(e1), 1e-8f));
+  e1[0] = __fdiv_rn(e1[0], d); e1[1] = __fdiv_rn(e1[1], d); e1[2] = __fdiv_rn(e1[2], d);
+  const float e2[3] = {__fsub_rn(__fmul_rn(e0[1], e1[2]), __fmul_rn(e0[2], e1[1])),
+                       __fsub_rn(__fmul_rn(e0[2], e1[0]), __fmul_rn(e0[0], e1[2])),
+                       __fsub_rn(__fmul_rn(e0[0], e1[1]), __fmul_rn(e0[1], e1[0]))};
 #pragma unroll
   for (int i = 0; i < 3; ++i) { R[i * 3 + 0] = e0[i]; R[i * 3 + 1] = e1[i]; R[i * 3 + 2] = e2[i]; }
 }
 
-// (sin, cos) of the torsion defined by 4 points a0..a3   (geometry.py:172-194)
+// (sin, cos) of the torsion defined by 4 points a0..a3   (geometry.py:172-194):
+// frame = from_3_points(a1, a2, a0); rel = frame.invert().apply(a3) = R^T a3 + (-(R^T a2))
+// (rigid_utils.py:1047-1085); sin = rel.z, cos = rel.y, normalised with +1e-8 under the root.
 __device__ __forceinline__ void torsion_sincos(const float* a0, const float* a1, const float* a2, const float* a3,
                                                float* out2) {
   float R[9];
   frame_from_3_points(a1, a2, a0, R);
-  const float dx = a3[0] - a2[0], dy = a3[1] - a2[1], dz = a3[2] - a2[2];
-  const float ry = R[1] * dx + R[4] * dy + R[7] * dz;     // (R^T d).y
-  const float rz = R[2] * dx + R[5] * dy + R[8] * dz;     // (R^T d).z
-  const float den = sqrtf(rz * rz + ry * ry + 1e-8f);
-  out2[0] = rz / den;
-  out2[1] = ry / den;
+  const float c1[3] = {R[1], R[4], R[7]}, c2[3] = {R[2], R[5], R[8]};     // rows 1, 2 of R^T
+  const float ry = __fadd_rn(dot3(c1, a3), -dot3(c1, a2));
+  const float rz = __fadd_rn(dot3(c2, a3), -dot3(c2, a2));
+  const float den = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(rz, rz), __fmul_rn(ry, ry)), 1e-8f));
+  out2[0] = __fdiv_rn(rz, den);
+  out2[1] = __fdiv_rn(ry, den);
 }
 
 __global__ void featurize_kernel(const float* __restrict__ atom14, const int64_t* __restrict__ seqres,

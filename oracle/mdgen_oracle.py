@@ -440,7 +440,8 @@ def featurize_atom14(atom14, seqres):
     pos = torch.cat([pre_omega[:, :, None], phi[:, :, None], psi[:, :, None], chis], 2)              # [B,L,7,4,3]
     tmask = torch.cat([pre_omega_m[..., None], phi_m[..., None], psi_m[..., None], chis_m], -1)
     fR, ft = from_3_points(pos[..., 1, :], pos[..., 2, :], pos[..., 0, :])                           # :172-177
-    rel = rot_vec_mul(fR.transpose(-1, -2), pos[..., 3, :] - ft)                                     # :179
+    fRt = fR.transpose(-1, -2)                                                                       # :179 invert().apply():
+    rel = rot_vec_mul(fRt, pos[..., 3, :]) + (-rot_vec_mul(fRt, ft))                                 # R^T p + (-(R^T o))
     sc = torch.stack([rel[..., 2], rel[..., 1]], -1)                                                 # :181-183
     sc = sc / torch.sqrt((sc * sc).sum(-1, keepdim=True) + 1e-8)                                     # :185-194
     sc = sc * torch.tensor([1.0, 1.0, -1.0, 1.0, 1.0, 1.0, 1.0])[None, None, :, None]                # :196-201
