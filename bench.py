@@ -48,6 +48,7 @@ def parse_args():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-torch-gpu", action="store_true", help="skip timing the stock-ATen port on the GPU")
     p.add_argument("--use-tc", type=int, default=-1, help="-1 = library default")
+    p.add_argument("--use-graph", type=int, default=-1, help="-1 = library default (CUDA-graph step replay for small workloads)")
     return p.parse_args()
 
 
@@ -229,6 +230,8 @@ def main():
     eng = m.model.engine()
     if a.use_tc >= 0:
         eng.set_option("use_tc", a.use_tc)
+    if a.use_graph >= 0:
+        eng.set_option("use_graph", a.use_graph)
     D = m.latent_dim
     # every rank samples its own shard of independent trajectories (different seeds per rank)
     hbatch = synthetic_batch(B, T, L, seed=rank_seed(1, rank), vary_frames=False)
@@ -382,6 +385,7 @@ def main():
                        "tokens_per_forward": N, "parallelism": f"dp{world} (independent trajectories, "
                        "no data-path collective)", "l2": "working set (>4 GB activations per forward) "
                        "far exceeds the 126 MB L2; no explicit flush needed",
+                       "graph_replays": eng.get_option("graph_replays"),
                        "gemm_path": ("tcgen05 " + ("bf16 operands (token GEMMs) / TF32 (attention), fp32 accumulate; "
                                      "IPA key-frame trunk fp32" if eng.get_option("gemm_bf16") else "TF32"))
                                     if use_tc else "fp32 SIMT"},

@@ -72,6 +72,11 @@ struct mdgen_handle {
 #endif
   int gemm_bf16 = 1;   // token GEMMs (QKV / out / fc1 / fc2) with bf16 operands (kind::f16); 0 = TF32 operands
   int emu_bf16 = 0;    // precision experiments: bit 0 MLP, bit 1 attention projections see bf16-rounded operands
+  int use_graph = 1;                 // replay steps from a CUDA graph when the workload is launch-bound
+  long long graph_max_tokens = 65536;
+  cudaStream_t gstream = nullptr;
+  cudaEvent_t gev_in = nullptr, gev_out = nullptr;
+  int64_t graph_launches_per_pair = 0, graph_replays = 0;
   bool trunk_precomputed = false;   // set by mdgen_sample_euler while the step loop runs
   int use_tc_attn = 1; // tcgen05 attention for sequences longer than 64 (needs use_tc)
   int tc_min_rows = 1024;   // fewer rows (the IPA key-frame trunk) stay on the exact-fp32 skinny GEMM  // below this many rows the SIMT GEMM is used (latency-bound shapes)
@@ -633,6 +638,7 @@ int mdgen_create(const mdgen_config* cfg, mdgen_handle** out) {
 
 void mdgen_destroy(mdgen_handle* h) {
   if (!h) return;
+  if (h->gstream) { cudaStreamDestroy(h->gstream); cudaEventDestroy(h->gev_in); cudaEventDestroy(h->gev_out); }
   for (void* p : h->allocs) cudaFree(p);
   for (auto& e : h->prof) { cudaEventDestroy(e.e0); cudaEventDestroy(e.e1); }
   delete h;
@@ -836,16 +842,84 @@ int mdgen_sample_euler(mdgen_handle* h, const float* zs, const float* t_grid, in
   step_set_kernel<<<1, 1, 0, s>>>(h->step, 0);
   CHECK_LAUNCH(h);
   // ping-pong Euler state: x_k in bufA/bufB alternately; the last step writes x_out
-  const float* cur = zs;
   float* bufA = h->xbuf;
   float* bufB = h->xbuf2;
-  for (int k = 0; k < K; ++k) {
+  auto one_step = [&](cudaStream_t st, const float* src, float* dst) -> int {
+    int rc = run_step(h, st, cond, src, dst, /*euler=*/true, h->step, /*bstride=*/0);
+    if (rc != MDGEN_OK) return rc;
+    step_advance_kernel<<<1, 1, 0, st>>>(h->step);
+    CHECK_LAUNCH(h);
+    return MDGEN_OK;
+  };
+  const long long Ntok = (long long)cond->B * cond->T * cond->L;
+  // Small workloads (e.g. sim_inference.py's one trajectory per call) are launch-bound: ~125 launches
+  // per step. Every step issues the same launch sequence (the step index lives in device memory), so
+  // steps 1..K-2 are replayed from a CUDA graph that holds one even/odd pair of steps. The graph runs on
+  // a private capturable stream (PyTorch's current stream is usually the un-capturable legacy stream),
+  // fenced against the caller's stream with events. Any capture failure falls back to eager launches.
+  const bool want_graph = h->use_graph && !h->profile && K >= 6 && Ntok <= h->graph_max_tokens;
+  int k = 0;
+  const float* cur = zs;
+  auto finish = [&](int rc) { h->trunk_precomputed = false; return rc; };
+  if (want_graph) {
+    if (!h->gstream) {
+      if (cudaStreamCreateWithFlags(&h->gstream, cudaStreamNonBlocking) != cudaSuccess ||
+          cudaEventCreateWithFlags(&h->gev_in, cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&h->gev_out, cudaEventDisableTiming) != cudaSuccess) {
+        h->gstream = nullptr;
+        (void)cudaGetLastError();
+      }
+    }
+  }
+  if (want_graph && h->gstream) {
+    cudaStream_t g = h->gstream;
+    CUDA_TRY(h, cudaEventRecord(h->gev_in, s));
+    CUDA_TRY(h, cudaStreamWaitEvent(g, h->gev_in, 0));
+    // step 0 eagerly (zs -> bufA): also performs every lazy allocation / attribute set of the step
+    int rc = one_step(g, zs, K == 1 ? x_out : bufA);
+    if (rc != MDGEN_OK) return finish(rc);
+    k = 1; cur = bufA;
+    const int pairs = (K - 2) / 2;              // steps 1 .. 2*pairs run from the graph, in (A->B, B->A) pairs
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    bool ok = cudaStreamBeginCapture(g, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    if (ok) {
+      const int64_t launches0 = h->launches;
+      int r1 = one_step(g, bufA, bufB);
+      int r2 = (r1 == MDGEN_OK) ? one_step(g, bufB, bufA) : r1;
+      cudaError_t ce = cudaStreamEndCapture(g, &graph);
+      ok = (r1 == MDGEN_OK && r2 == MDGEN_OK && ce == cudaSuccess && graph != nullptr);
+      h->graph_launches_per_pair = h->launches - launches0;
+      h->launches = launches0;                   // captured, not yet executed
+      if (ok) ok = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+    }
+    (void)cudaGetLastError();
+    if (ok) {
+      for (int p = 0; p < pairs && ok; ++p) {
+        ok = cudaGraphLaunch(exec, g) == cudaSuccess;
+        if (ok) { k += 2; h->launches += h->graph_launches_per_pair; }
+      }
+      h->graph_replays += pairs;
+    }
+    if (exec) cudaGraphExecDestroy(exec);
+    if (graph) cudaGraphDestroy(graph);
+    (void)cudaGetLastError();
+    // remaining steps (and everything, if the graph could not be built) eagerly on the same stream
+    for (; k < K; ++k) {
+      float* nxt = (k == K - 1) ? x_out : ((k & 1) == 0 ? bufA : bufB);
+      rc = one_step(g, cur, nxt);
+      if (rc != MDGEN_OK) return finish(rc);
+      cur = nxt;
+    }
+    CUDA_TRY(h, cudaEventRecord(h->gev_out, g));
+    CUDA_TRY(h, cudaStreamWaitEvent(s, h->gev_out, 0));
+    return finish(MDGEN_OK);
+  }
+  for (; k < K; ++k) {
     float* nxt = (k == K - 1) ? x_out : ((k & 1) == 0 ? bufA : bufB);
     // (K == 1 with x_out == zs updates in place: each state element is read and written by the same thread)
-    int rc = run_step(h, s, cond, cur, nxt, /*euler=*/true, h->step, /*bstride=*/0);
-    if (rc != MDGEN_OK) { h->trunk_precomputed = false; return rc; }
-    step_advance_kernel<<<1, 1, 0, s>>>(h->step);
-    CHECK_LAUNCH(h);
+    int rc = one_step(s, cur, nxt);
+    if (rc != MDGEN_OK) return finish(rc);
     cur = nxt;
   }
   h->trunk_precomputed = false;
@@ -943,6 +1017,8 @@ int mdgen_set_option(mdgen_handle* h, const char* key, int64_t value) {
   else if (k == "use_tc_attn") h->use_tc_attn = (int)value;
   else if (k == "emu_bf16") h->emu_bf16 = (int)value;
   else if (k == "gemm_bf16") h->gemm_bf16 = (int)value;
+  else if (k == "use_graph") h->use_graph = (int)value;
+  else if (k == "graph_max_tokens") h->graph_max_tokens = value;
   else if (k == "profile") {
     h->profile = (int)value;
     if (!value) {
@@ -960,6 +1036,8 @@ int64_t mdgen_get_option(const mdgen_handle* h, const char* key) {
   if (k == "tc_min_rows") return h->tc_min_rows;
   if (k == "use_tc_attn") return h->use_tc_attn;
   if (k == "gemm_bf16") return h->gemm_bf16;
+  if (k == "use_graph") return h->use_graph;
+  if (k == "graph_replays") return h->graph_replays;
   if (k == "profile") return h->profile;
   if (k == "modw") return h->modw;
   return -1;
