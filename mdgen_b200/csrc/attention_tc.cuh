@@ -2,7 +2,7 @@
 // softmax(Q K^T + key-padding) V with bias-KV token and RoPE, scores never leave the SM
 // (restates mdgen/model/mha.py:260-397; K8-K13 of SURVEY.md §2c collapse into this kernel).
 //
-// One CTA = one (sequence, head, 128-query tile); 160 threads, two CTAs per SM (256 TMEM columns and
+// One CTA = one (sequence, head, 128-query tile); 320 threads, two CTAs per SM (256 TMEM columns and
 // ~95 KB of shared memory each). Inside a CTA the tensor pipe runs ahead of / behind the softmax:
 // S is double buffered in TMEM (QK^T of tile g+1 is issued before the softmax of tile g starts) and
 // O accumulates in TMEM across key tiles (P·V of tile g runs while tile g+1 is exponentiated), so
@@ -12,7 +12,7 @@
 //                          K-major SWIZZLE_128B, plus additive key mask and |k| bound) in a global
 //                          scratch; the CTAs of all query tiles of that (sequence, head) are adjacent
 //                          in the grid, so they share those images through L2.
-//   warp 4 lane 0        : producer - one cp.async.bulk (TMA 1-D) per key tile refills a 3-stage
+//   warp 8 lane 0        : producer - one cp.async.bulk (TMA 1-D) per key tile refills a 3-stage
 //                          shared-memory ring from that scratch.
 //   warp 9 lane 0        : the single MMA-issuing thread (tcgen05.mma + tcgen05.commit).
 //   warps 0-7  "softmax" : warp w owns the 32 query rows of TMEM lane quarter (w & 3) and the column
@@ -22,8 +22,9 @@
 //                          a row only exchange data on the rare exact-max path and in the epilogue.
 // Per key tile:  S[128x96] = Q·K^T    (3 x tcgen05.mma kind::tf32, K = 24 = 3 x 8, A/B from smem)
 //                P = exp2(S - m)      (softmax warps, TMEM -> regs -> TMEM, in place)
-//                O_t[128x32] = P·V    (12 x tcgen05.mma kind::tf32, A = P from TMEM, B = V^T smem)
-//                O (TMEM) += P·V; rescaled in place only when a row's softmax reference moves
+//                O[128x32] += P·V     (12 x tcgen05.mma kind::tf32, A = P from TMEM, B = V^T smem);
+//                                     O lives in TMEM and is rescaled in place only when a row's softmax
+//                                     reference moves
 // Online softmax reference: the exact two-pass (row max, then exp) is used for a tile only when the
 // row has no reference yet or when the Cauchy-Schwarz bound |q_i|*max_j|k_j| could exceed the
 // reference by 2^100; otherwise the tile is exponentiated in a single TMEM pass against the

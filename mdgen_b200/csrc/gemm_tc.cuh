@@ -1,20 +1,21 @@
-// tcgen05 TF32 GEMM for the token-wise linear layers (QKV / out-proj / fc1 / fc2: 75 % of the
-// denoiser FLOPs):   out = epilogue( A[M,K] · W[N,K]^T + bias )      fp32 accumulate in TMEM.
+// tcgen05 GEMM for the token-wise linear layers (QKV / out-proj / fc1 / fc2: 75 % of the denoiser
+// FLOPs):   out = epilogue( A[M,K] · W[N,K]^T + bias )      fp32 accumulate in TMEM.
+// Operands are bf16 (kind::f16, default) or TF32-in-fp32 (kind::tf32); both use the same code path.
 //
 // Blackwell-native structure (sm_100a only):
-//   * persistent CTAs (grid = #SMs), static round-robin tile scheduler, tiles 128 x 192, K-block
-//     32 fp32 (= one 128-byte swizzle row)
-//   * warp 0: TMA producer (cp.async.bulk.tensor.2d, SWIZZLE_128B, 5-stage mbarrier ring)
-//   * warp 1: single-thread tcgen05.mma.cta_group::1.kind::tf32 issuer, A and B from shared memory
-//     through UMMA descriptors, accumulators in TMEM (2 x 192 columns, double buffered so the
-//     epilogue of tile i overlaps the MMAs of tile i+1)
+//   * persistent CTAs (grid = #SMs), static round-robin tile scheduler, tiles 128 x 192, K-block =
+//     one 128-byte swizzle row (64 bf16 or 32 fp32 elements)
+//   * warp 0: TMA producer (cp.async.bulk.tensor.2d, SWIZZLE_128B, 4-stage mbarrier ring)
+//   * warp 1: single-thread tcgen05.mma.cta_group::1 issuer, A and B from shared memory through UMMA
+//     descriptors, accumulators in TMEM (2 x 192 columns, double buffered so the epilogue of tile i
+//     overlaps the MMAs of tile i+1)
 //   * warp 2: TMEM allocator;  warps 4-11 (residual epilogues) / 4-15 (store, GELU): epilogue. Each warp
 //     owns a TMEM lane quarter and a 96- / 64-column slice of the tile: tcgen05.ld 32x32b (thread = row) -> per-warp shared-memory transpose
 //     -> fused bias / GELU / gate*y+residual on *row-contiguous* float4s -> fully coalesced
 //     128-bit global loads/stores (4 x 128-byte lines per warp instruction)
-// Operands are fp32 bit patterns already rounded to TF32 (round-to-nearest) by their producers
-// (weights at pack time, activations by the LN / attention / GELU epilogues), so the tensor core's
-// truncation of the low 13 mantissa bits is exact.
+// TF32 mode: operands are fp32 bit patterns already rounded to TF32 (round-to-nearest) by their
+// producers (weights at pack time, activations by the LN / attention / GELU epilogues), so the tensor
+// core's truncation of the low 13 mantissa bits is exact. bf16 mode: the producers store bf16.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
