@@ -50,7 +50,7 @@ constexpr int AT_IMG_BYTES = AT_K_BYTES + AT_VT_BYTES + AT_KM_FLOATS * 4;   // o
 constexpr int AT_STAGE_BYTES = 26 * 1024;       // smem stage pitch (keeps K / V^T 1024-byte aligned)
 constexpr int AT_STAGES = 3;
 constexpr int AT_SMEM_BYTES = 1024 /*align*/ + AT_Q_BYTES + AT_STAGES * AT_STAGE_BYTES + 128 /*barriers*/ + 4 * 512 /*row exchange*/;
-constexpr int AT_TMEM_COLS = 256;               // S/P double buffer: cols [0,96) [96,192); O: cols [192,224)
+constexpr int AT_TMEM_COLS = 256;               // S/P double buffer: cols [0,96) [96,192); O_even / O_odd: cols [192,224) [224,256)
 
 __device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&v)[32]) {
   asm volatile(
@@ -305,7 +305,9 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(AttnParams p, co
 #pragma unroll
         for (int ks = 0; ks < AT_KT / 8; ++ks) {
           const uint64_t bdesc = umma_desc_k128(vb + (ks >> 2) * 4096 + (ks & 3) * 32);
-          tc_mma_tf32_ts(tmem_O, tmem_S + 8 * ks, bdesc, idesc_pv, (uint32_t)((g | ks) != 0));
+          // two independent accumulation chains (even / odd k-steps -> O_even / O_odd) halve the length of
+          // the dependent-MMA chain of this small (N = 32) product; the epilogue adds the two halves
+          tc_mma_tf32_ts(tmem_O + (ks & 1) * 32, tmem_S + 8 * ks, bdesc, idesc_pv, (uint32_t)((g | (ks >> 1)) != 0));
         }
         tc_commit(b_kvfree(st));                   // K/V stage reusable once the PV MMAs retire
         tc_commit(b_odone);
@@ -396,13 +398,14 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(AttnParams p, co
         mbar_wait(b_odone, (uint32_t)((g - 1) & 1));   // P·V of every earlier tile has retired
         tc_fence_after();
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
+        for (int c = 0; c < 6; ++c) {          // 3 x 8 columns of O_even, then of O_odd
+          const uint32_t col = (uint32_t)((c / 3) * 32 + (c % 3) * 8);
           uint32_t o[8];
-          tc_ld8(tmem_O + lane_addr + 8 * c, o);
+          tc_ld8(tmem_O + lane_addr + col, o);
           tc_ld_wait();
 #pragma unroll
           for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          tc_st8(tmem_O + lane_addr + 8 * c, o);
+          tc_st8(tmem_O + lane_addr + col, o);
         }
       }
       tc_st_wait();
@@ -419,10 +422,13 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(AttnParams p, co
       const float l_tot = l_run + xch[128 * 3 + row];
       mbar_wait(b_odone, (uint32_t)((nkt - 1) & 1));
       tc_fence_after();
-      uint32_t o0[8], o1[8], o2[8];
+      uint32_t o0[8], o1[8], o2[8], p0[8], p1[8], p2[8];
       tc_ld8(tmem_O + lane_addr + 0, o0);
       tc_ld8(tmem_O + lane_addr + 8, o1);
       tc_ld8(tmem_O + lane_addr + 16, o2);
+      tc_ld8(tmem_O + lane_addr + 32, p0);
+      tc_ld8(tmem_O + lane_addr + 40, p1);
+      tc_ld8(tmem_O + lane_addr + 48, p2);
       tc_ld_wait();
       if (qok2) {
         const long long tq2 = seq_token(sm, s, e2);
@@ -430,8 +436,9 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(AttnParams p, co
         float acc[kHD];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          acc[i] = __uint_as_float(o0[i]) * inv; acc[8 + i] = __uint_as_float(o1[i]) * inv;
-          acc[16 + i] = __uint_as_float(o2[i]) * inv;
+          acc[i] = (__uint_as_float(o0[i]) + __uint_as_float(p0[i])) * inv;
+          acc[8 + i] = (__uint_as_float(o1[i]) + __uint_as_float(p1[i])) * inv;
+          acc[16 + i] = (__uint_as_float(o2[i]) + __uint_as_float(p2[i])) * inv;
         }
 #pragma unroll
         for (int i = 0; i < 6; ++i)
