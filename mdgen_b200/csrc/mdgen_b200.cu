@@ -79,6 +79,11 @@ struct mdgen_handle {
   int64_t graph_launches_per_pair = 0, graph_replays = 0;
   bool trunk_precomputed = false;   // set by mdgen_sample_euler while the step loop runs
   int use_tc_attn = 1; // tcgen05 attention for sequences longer than 64 (needs use_tc)
+#ifdef MDGEN_NO_TC
+  int attn_variant = 0;
+#else
+  int attn_variant = kAttnVariantDefault;   // build variant of the tcgen05 attention (attention_tc.cuh: attn_tc_launch)
+#endif
   int tc_min_rows = 1024;   // fewer rows (the IPA key-frame trunk) stay on the exact-fp32 skinny GEMM  // below this many rows the SIMT GEMM is used (latency-bound shapes)
   int profile = 0;
   std::vector<ProfEntry> prof;
@@ -389,7 +394,7 @@ int attention(mdgen_handle* h, cudaStream_t s, const float* qkv, const float* ma
       CUDA_TRY(h, cudaMemsetAsync(h->attn_scratch, 0, need, s));   // V^T pad rows must read as zeros
       h->attn_scratch_bytes = need;
     }
-    if (attn_tc_launch(p, h->attn_scratch, s, &h->err)) return MDGEN_E_CUDA;
+    if (attn_tc_launch(p, h->attn_scratch, h->attn_variant, s, &h->err)) return MDGEN_E_CUDA;
     h->launches += 2;
     return MDGEN_OK;
   }
@@ -1015,6 +1020,7 @@ int mdgen_set_option(mdgen_handle* h, const char* key, int64_t value) {
     h->use_tc = (int)value;
   } else if (k == "tc_min_rows") h->tc_min_rows = (int)value;
   else if (k == "use_tc_attn") h->use_tc_attn = (int)value;
+  else if (k == "attn_variant") h->attn_variant = (int)value & 127;
   else if (k == "emu_bf16") h->emu_bf16 = (int)value;
   else if (k == "gemm_bf16") h->gemm_bf16 = (int)value;
   else if (k == "use_graph") h->use_graph = (int)value;
@@ -1035,6 +1041,7 @@ int64_t mdgen_get_option(const mdgen_handle* h, const char* key) {
   if (k == "use_tc") return h->use_tc;
   if (k == "tc_min_rows") return h->tc_min_rows;
   if (k == "use_tc_attn") return h->use_tc_attn;
+  if (k == "attn_variant") return h->attn_variant;
   if (k == "gemm_bf16") return h->gemm_bf16;
   if (k == "use_graph") return h->use_graph;
   if (k == "graph_replays") return h->graph_replays;

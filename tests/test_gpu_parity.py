@@ -79,10 +79,11 @@ def test_golden_cases(name, path):
     assert (aa.cpu().numpy() == g["aa_out"]).all()
 
 
-@pytest.mark.parametrize("path", PATHS)
-@pytest.mark.parametrize("shape", [(1, 300, 4, 4), (2, 40, 70, 3), (1, 130, 33, 2)])
-def test_oracle_other_shapes(shape, path):
-    """Long time axis (flash path, ragged tiles), long residue axis, odd sizes, padding."""
+_ORACLE_CACHE = {}
+
+
+def _oracle_shape_case(shape):
+    """Synthetic case at `shape` = (B, T, L, K) and the CPU oracle's Euler state for it (cached per shape)."""
     from mdgen_b200.config import config_from_args, default_args
     from oracle import mdgen_oracle as O
     B, T, L, K = shape
@@ -92,19 +93,46 @@ def test_oracle_other_shapes(shape, path):
     sd = synthetic_state_dict(cfg, seed=0)
     batch = synthetic_batch(B, T, L, seed=3, pad_last=(5 if L > 8 else 0))
     zs = synthetic_noise(B, T, L, cfg.latent_dim, seed=4)
+    if shape not in _ORACLE_CACHE:
+        op = O.prep_batch(cfg, batch)
+        kw = dict(mask=op["mask"], start=op["start"], end=op["end"], x_cond=op["x_cond"],
+                  x_cond_mask=op["x_cond_mask"], aatype=op["aatype"])
+        with torch.no_grad():
+            xo = O.sample_euler(sd, cfg, zs, euler_time_grid(K), **kw)
+        _ORACLE_CACHE[shape] = (op["latents"], xo)
+    return args, sd, batch, zs, _ORACLE_CACHE[shape]
+
+
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("shape", [(1, 300, 4, 4), (2, 40, 70, 3), (1, 130, 33, 2)])
+def test_oracle_other_shapes(shape, path):
+    """Long time axis (flash path, ragged tiles), long residue axis, odd sizes, padding."""
+    args, sd, batch, zs, (lat_o, xo) = _oracle_shape_case(shape)
     m = _wrapper(args, sd, path)
     prep = m.prep_batch(_dev(batch))
-    xk = m.model.sample_euler(zs.cuda(), euler_time_grid(K), **prep["model_kwargs"])
-    op = O.prep_batch(cfg, batch)
-    kw = dict(mask=op["mask"], start=op["start"], end=op["end"], x_cond=op["x_cond"],
-              x_cond_mask=op["x_cond_mask"], aatype=op["aatype"])
-    torch.set_num_threads(max(1, torch.get_num_threads()))
-    with torch.no_grad():
-        xo = O.sample_euler(sd, cfg, zs, euler_time_grid(K), **kw)
-    assert max_rel(prep["latents"].cpu(), op["latents"]) < TOL_GEOM
+    xk = m.model.sample_euler(zs.cuda(), euler_time_grid(shape[3]), **prep["model_kwargs"])
+    assert max_rel(prep["latents"].cpu(), lat_o) < TOL_GEOM
     tol = TOL_SIMT if path == "simt" else TOL
     assert max_rel(xk.cpu(), xo) < tol, max_rel(xk.cpu(), xo)
     assert rel_l2(xk.cpu(), xo) < tol
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 6, 14])
+@pytest.mark.parametrize("shape", [(1, 300, 4, 4), (2, 40, 70, 3), (5, 300, 4, 2)])
+def test_attention_variants_match_oracle(shape, variant):
+    """Every build variant of the tcgen05 attention kernels (option `attn_variant`: bit 0 bf16 P.V, bit 1 staged
+    pre-pass, bit 2 persistent kernel, bit 3 persistent with 12 softmax warps; 3 is the default) against the
+    oracle: frame attention over 300 frames (3 query tiles, ragged key tiles; with B = 5 there are 960 work
+    items, so every persistent CTA walks through several of them) and residue attention over 70 residues with
+    padded (masked) keys."""
+    args, sd, batch, zs, (_, xo) = _oracle_shape_case(shape)
+    m = _wrapper(args, sd, "bf16")
+    m.model.engine().set_option("attn_variant", variant)
+    assert m.model.engine().get_option("attn_variant") == variant
+    prep = m.prep_batch(_dev(batch))
+    xk = m.model.sample_euler(zs.cuda(), euler_time_grid(shape[3]), **prep["model_kwargs"])
+    assert max_rel(xk.cpu(), xo) < TOL, max_rel(xk.cpu(), xo)
+    assert rel_l2(xk.cpu(), xo) < TOL
 
 
 def test_no_cpu_fallback():
