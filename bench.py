@@ -312,16 +312,17 @@ def main():
     use_tc = eng.get_option("use_tc")
     fam_tflops = {k: round(fam_flops[k] / (prof[k][0] / prof[k][1] / 1e3) / 1e12, 1) for k in fam_flops if k in prof}
     # DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/r1_attention_ncu.md:
-    # attn_tc_kernel 1.53 GB read + 0.19 GB write, attn_prep_kernel 0.79 + 0.81 GB) — valid for this workload only
-    traffic = 3.32e9 if (dom == "mha_t" and (B, T, L) == (64, 1000, 4)) else None
+    # attn_tc_kernel<PV16> 1.14 GB read + 0.19 GB write, attn_prep2_kernel 0.40 + 0.60 GB) — valid for this workload only
+    traffic = 2.33e9 if (dom == "mha_t" and (B, T, L) == (64, 1000, 4)) else None
     roofline = {
         "kernel": dom, "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
         "frac": achieved / peak, "traffic": traffic, "family_tflops": fam_tflops,
-        "note": "mha_t = attn_prep_kernel + attn_tc_kernel; at head_dim 24 it is bound by the MUFU ex2 pipe "
-                "(96 MMA FLOP per exponential), see profiles/r1_attention_ncu.md; the GEMM families' "
+        "note": "mha_t = attn_prep2_kernel + attn_tc_kernel; at head_dim 24 it is bound by TMEM read bandwidth "
+                "(every fp32 score is read back once: 64 B/clk/SM) and the MUFU ex2 pipe (96 MMA FLOP per "
+                "exponential), not by the tensor pipe - see profiles/r1_attention_ncu.md; the GEMM families' "
                 "achieved TFLOP/s are in family_tflops",
         "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']}); "
-                       + ("token GEMMs: bf16 operands (kind::f16), attention: TF32 operands (half that peak)"
+                       + ("token GEMMs and attention P.V: bf16 operands (kind::f16), attention Q.K^T: TF32 operands"
                           if use_tc else "fp32 SIMT FMA (validation path), not the tensor pipe"),
         "avg_launch_ms": dom_ms, "launches": prof[dom][1], "time_shares": shares,
         "whole_step_tflops": flops_forward(N, T, L) * K / (ms_per_step / 1e3) / 1e12,
