@@ -151,26 +151,44 @@ __global__ void __launch_bounds__(kC) embed_kernel(
   float bsum = (MODE == 0) ? (bias0[c] + bias1[c]) : 0.f;
   if (MODE == 1 && step_ptr) ipa += (size_t)(*step_ptr) * ipa_step_stride;   // trunk output of this Euler step
   __syncthreads();
-  for (int i = 0; i < nt; ++i) {
-    long long n = n0 + i;
-    float s = 0.f;
+  // sample index / residue index of the block's first token; per-token values follow incrementally
+  // (a 64-bit division per token and thread used to dominate this kernel)
+  const long long TL = (long long)T * L;
+  long long b0 = n0 / TL;
+  long long rem0 = n0 - b0 * TL;
+  const int l0 = (int)(n0 % L);
+  constexpr int U = 4;                 // tokens in flight per thread (independent global loads)
+  for (int i = 0; i < nt; i += U) {
+    float add[U];
 #pragma unroll
-    for (int k4 = 0; k4 < 7; ++k4) {     // 128-bit broadcast reads of the token's latent (w[k] = 0 for k >= D)
-      const float4 xv = *reinterpret_cast<const float4*>(&xs[i][4 * k4]);
-      s = fmaf(w[4 * k4], xv.x, s); s = fmaf(w[4 * k4 + 1], xv.y, s);
-      s = fmaf(w[4 * k4 + 2], xv.z, s); s = fmaf(w[4 * k4 + 3], xv.w, s);
+    for (int u = 0; u < U; ++u) {
+      add[u] = 0.f;
+      if (i + u < nt) {
+        const long long n = n0 + i + u;
+        const int l = (l0 + i + u) % L;
+        if (MODE == 0) {
+          add[u] = bsum + emask[(size_t)ms[i + u] * kC + c];
+          if (pos) add[u] += pos[(size_t)l * kC + c];
+        } else {
+          long long b = b0, rem = rem0 + i + u;
+          while (rem >= TL) { rem -= TL; ++b; }
+          add[u] = cond[(size_t)n * kC + c] + ipa[((size_t)b * L + l) * kC + c];
+        }
+      }
     }
-    if (MODE == 0) {
-      int l = (int)(n % L);
-      s += bsum;
-      if (pos) s += pos[(size_t)l * kC + c];
-      s += emask[(size_t)ms[i] * kC + c];
-    } else {
-      long long b = n / ((long long)T * L);
-      int l = (int)(n % L);
-      s += cond[(size_t)n * kC + c] + ipa[((size_t)b * L + l) * kC + c];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (i + u < nt) {
+        float s = 0.f;
+#pragma unroll
+        for (int k4 = 0; k4 < 7; ++k4) {     // 128-bit broadcast reads of the token's latent (w[k] = 0 for k >= D)
+          const float4 xv = *reinterpret_cast<const float4*>(&xs[i + u][4 * k4]);
+          s = fmaf(w[4 * k4], xv.x, s); s = fmaf(w[4 * k4 + 1], xv.y, s);
+          s = fmaf(w[4 * k4 + 2], xv.z, s); s = fmaf(w[4 * k4 + 3], xv.w, s);
+        }
+        out[(size_t)(n0 + i + u) * kC + c] = s + add[u];
+      }
     }
-    out[(size_t)n * kC + c] = s;
   }
 }
 
@@ -180,6 +198,22 @@ __global__ void __launch_bounds__(kC) embed_kernel(
 //   EULER = true : x_out[n,:] = x_in[n,:] + dt[*step] * v      (state stays fp32)
 //   EULER = false: x_out[n,:] = v
 // One warp per token; W [D,C] (<= 43 KB) is staged in shared memory once per block.
+// reduces p[j] over the 32 lanes for all j at once: afterwards lane j holds sum_lanes p[j] (31 shuffles
+// instead of 32 x 5 for one warp_sum per output)
+__device__ __forceinline__ float warp_transpose_reduce32(float (&p)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool hi = (lane & off) != 0;
+#pragma unroll
+    for (int k = 0; k < off; ++k) {
+      const float send = hi ? p[k] : p[k + off];
+      const float keep = hi ? p[k + off] : p[k];
+      p[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return p[0];
+}
+
 template <bool EULER>
 __global__ void __launch_bounds__(256) final_kernel(
     const float* __restrict__ h, ModRef mod, int shift_off, int scale_off,
@@ -189,55 +223,74 @@ __global__ void __launch_bounds__(256) final_kernel(
   extern __shared__ float ws[];  // [D][C]
   for (int i = threadIdx.x; i < D * kC; i += blockDim.x) ws[i] = W[i];
   __syncthreads();
-  int lane = threadIdx.x & 31;
-  int wid = threadIdx.x >> 5;
-  int nw = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int wid = threadIdx.x >> 5;
+  const int nw = blockDim.x >> 5;
   float step_dt = 0.f;
   if (EULER) step_dt = dt[mod.step_ptr ? *mod.step_ptr : 0];
-  for (long long tok = (long long)blockIdx.x * nw + wid; tok < N; tok += (long long)gridDim.x * nw) {
-    const float4* xr = reinterpret_cast<const float4*>(h + (size_t)tok * kC);
-    float4 v[3];
+  const float my_bias = lane < D ? bias[lane] : 0.f;
+  constexpr int TK = 2;   // tokens per warp pass: every weight row read from shared memory serves both
+  for (long long tok0 = ((long long)blockIdx.x * nw + wid) * TK; tok0 < N; tok0 += (long long)gridDim.x * nw * TK) {
+    float4 v[TK][3];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) v[i] = xr[i * 32 + lane];
-    float s = 0.f;
+    for (int t = 0; t < TK; ++t) {
+      const long long tok = tok0 + t < N ? tok0 + t : tok0;       // (odd tail: recompute the first token)
+      const float4* xr = reinterpret_cast<const float4*>(h + (size_t)tok * kC);
 #pragma unroll
-    for (int i = 0; i < 3; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-    float mean = warp_sum(s) * (1.0f / kC);
-    float q = 0.f;
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-      q += (a * a + b * b) + (c * c + d * d);
+      for (int i = 0; i < 3; ++i) v[t][i] = xr[i * 32 + lane];
     }
-    float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / kC) + 1e-6f);
-    const float* mr = mod_row(mod, tok);
-    const float4* sh = reinterpret_cast<const float4*>(mr + shift_off);
-    const float4* sc = reinterpret_cast<const float4*>(mr + scale_off);
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      float4 a = sh[i * 32 + lane], b = sc[i * 32 + lane];
-      v[i].x = (v[i].x - mean) * rstd * (1.0f + b.x) + a.x;
-      v[i].y = (v[i].y - mean) * rstd * (1.0f + b.y) + a.y;
-      v[i].z = (v[i].z - mean) * rstd * (1.0f + b.z) + a.z;
-      v[i].w = (v[i].w - mean) * rstd * (1.0f + b.w) + a.w;
-    }
-    float mine = 0.f;  // lane d keeps output d
-    for (int d = 0; d < D; ++d) {
-      const float4* wr = reinterpret_cast<const float4*>(ws + d * kC);
-      float p = 0.f;
+    for (int t = 0; t < TK; ++t) {
+      const long long tok = tok0 + t < N ? tok0 + t : tok0;
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) s += (v[t][i].x + v[t][i].y) + (v[t][i].z + v[t][i].w);
+      const float mean = warp_sum(s) * (1.0f / kC);
+      float q = 0.f;
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
-        float4 w4 = wr[i * 32 + lane];
-        p = fmaf(v[i].x, w4.x, p); p = fmaf(v[i].y, w4.y, p);
-        p = fmaf(v[i].z, w4.z, p); p = fmaf(v[i].w, w4.w, p);
+        float a = v[t][i].x - mean, b = v[t][i].y - mean, c = v[t][i].z - mean, d = v[t][i].w - mean;
+        q += (a * a + b * b) + (c * c + d * d);
       }
-      p = warp_sum(p);
-      if (lane == d) mine = p;
+      const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / kC) + 1e-6f);
+      const float* mr = mod_row(mod, tok);
+      const float4* sh = reinterpret_cast<const float4*>(mr + shift_off);
+      const float4* sc = reinterpret_cast<const float4*>(mr + scale_off);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const float4 a = sh[i * 32 + lane], b = sc[i * 32 + lane];
+        v[t][i].x = (v[t][i].x - mean) * rstd * (1.0f + b.x) + a.x;
+        v[t][i].y = (v[t][i].y - mean) * rstd * (1.0f + b.y) + a.y;
+        v[t][i].z = (v[t][i].z - mean) * rstd * (1.0f + b.z) + a.z;
+        v[t][i].w = (v[t][i].w - mean) * rstd * (1.0f + b.w) + a.w;
+      }
     }
-    if (lane < D) {
-      float vout = mine + bias[lane];
-      size_t o = (size_t)tok * D + lane;
-      x_out[o] = EULER ? fmaf(step_dt, vout, x_in[o]) : vout;
+    float p[TK][32];
+#pragma unroll
+    for (int d = 0; d < 32; ++d) {
+#pragma unroll
+      for (int t = 0; t < TK; ++t) p[t][d] = 0.f;
+      if (d < 28 && d < D) {
+        const float4* wr = reinterpret_cast<const float4*>(ws + d * kC);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const float4 w4 = wr[i * 32 + lane];
+#pragma unroll
+          for (int t = 0; t < TK; ++t) {
+            p[t][d] = fmaf(v[t][i].x, w4.x, p[t][d]); p[t][d] = fmaf(v[t][i].y, w4.y, p[t][d]);
+            p[t][d] = fmaf(v[t][i].z, w4.z, p[t][d]); p[t][d] = fmaf(v[t][i].w, w4.w, p[t][d]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < TK; ++t) {
+      const float mine = warp_transpose_reduce32(p[t], lane);     // lane d holds output d
+      if (lane < D && tok0 + t < N) {
+        const float vout = mine + my_bias;
+        const size_t o = (size_t)(tok0 + t) * D + lane;
+        x_out[o] = EULER ? fmaf(step_dt, vout, x_in[o]) : vout;
+      }
     }
   }
 }
