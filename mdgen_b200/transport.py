@@ -4,7 +4,9 @@ path uses (velocity prediction, GVP/Linear path => t in [0,1], mdgen/transport/t
 convention `sample_fn(zs, model_fn, **model_kwargs)`; when `model_fn` is (a functools.partial of)
 our `LatentMDGenModel.forward_inference`, the whole fixed-grid Euler loop
 (mdgen/transport/integrators.py:90-113) runs natively in libmdgen_b200 and only the final state
-is produced (the reference stacks every step and the caller takes [-1], wrapper.py:444-447)."""
+is produced (the reference stacks every step and the caller takes [-1], wrapper.py:444-447).
+`sample_ode('dopri5')` - the reference's default - drives the same fused forward (mdgen_forward) from the
+adaptive Dormand-Prince integrator of mdgen_b200/ode.py."""
 from __future__ import annotations
 
 import functools
@@ -27,13 +29,14 @@ class _LastOnly:
 class Sampler:
     def __init__(self, transport=None):
         self.transport = transport
+        self.last_stats = {}      # nfe / accepted / rejected / steps of the last dopri5 call
 
     def sample_ode(self, *, sampling_method="dopri5", num_steps=50, atol=1e-6, rtol=1e-3,
                    reverse=False):
-        if sampling_method != "euler":
+        if sampling_method not in ("euler", "dopri5"):
             raise NotImplementedError(
-                "mdgen_b200: only the fixed-grid Euler sampler is native; the adaptive dopri5 "
-                "sampler is a 'next' row (SURVEY.md §8f-2)")
+                f"mdgen_b200: sampling_method {sampling_method!r} is not implemented (euler: native loop, "
+                "dopri5: adaptive integrator around the native forward)")
         if reverse:
             raise NotImplementedError("reverse-time sampling is not used by the hot path")
         t_grid = torch.linspace(0.0, 1.0, num_steps)          # integrators.py:90 (t0=0, t1=1)
@@ -46,7 +49,17 @@ class Sampler:
             owner = getattr(fn, "__self__", None)
             if owner is None or not hasattr(owner, "sample_euler"):
                 raise NotImplementedError("sample_ode needs LatentMDGenModel.forward_inference")
-            return _LastOnly(owner.sample_euler(x, t_grid, **kw))
+            if sampling_method == "euler":
+                return _LastOnly(owner.sample_euler(x, t_grid, **kw))
+            from .ode import dopri5_integrate
+
+            def rhs(t, y):                                     # integrators.py:98-101: t * ones(B)
+                tb = torch.full((y.shape[0],), float(t), dtype=torch.float32, device=y.device)
+                return owner.forward_inference(y, tb, **kw)
+
+            self.last_stats = {}
+            return _LastOnly(dopri5_integrate(rhs, x, t_grid.tolist(), rtol=rtol, atol=atol,
+                                              last_only=True, stats=self.last_stats))
 
         return sample
 

@@ -12,8 +12,11 @@ Pinned by tests/golden/*.npz, which were produced by running the UNMODIFIED refe
 tests/golden/gen_golden.py and tests/test_oracle_golden.py.
 
 Third-party arithmetic the reference delegates to un-vendored packages (fair-esm rotary
-embedding, torchdiffeq fixed-grid Euler) is restated from the packages' published algorithms:
-"parity unpinned by the reference" for those two pieces.
+embedding, torchdiffeq fixed-grid Euler and adaptive dopri5) is restated from the packages' published
+algorithms: "parity unpinned by the reference" for those pieces. The dopri5 restatement
+(`sample_dopri5`, `dopri5_replay`) additionally has no live torchdiffeq to be checked against in this image: its
+Butcher tableau is pinned against scipy's independent RK45 tableau and its dense output against the defining
+interpolation conditions (tests/test_ode_cpu.py); the step controller follows torchdiffeq 0.2.x from its source.
 
 Never imported by mdgen_b200/ (the product).
 """
@@ -306,6 +309,118 @@ def sample_euler(sd, cfg, zs, t_grid, **kw):
         tv = torch.ones(B, device=zs.device) * t0.to(zs.device)                       # integrators.py:99
         x = x + (t1 - t0).to(zs.device) * forward(sd, cfg, x, tv, **kw)
     return x
+
+
+# --------------------------------------------------------------------------- adaptive sampler (default of the reference)
+# torchdiffeq.odeint(..., method='dopri5') as called by mdgen/transport/integrators.py:106-113 with
+# rtol 1e-3 / atol 1e-6 (mdgen/transport/transport.py:411-414). torchdiffeq 0.2.x, _impl/dopri5.py:
+_DP_ALPHA = torch.tensor([1 / 5, 3 / 10, 4 / 5, 8 / 9, 1.0, 1.0], dtype=torch.float64)
+_DP_BETA = torch.zeros(6, 7, dtype=torch.float64)
+for _i, _row in enumerate([[1 / 5], [3 / 40, 9 / 40], [44 / 45, -56 / 15, 32 / 9],
+                           [19372 / 6561, -25360 / 2187, 64448 / 6561, -212 / 729],
+                           [9017 / 3168, -355 / 33, 46732 / 5247, 49 / 176, -5103 / 18656],
+                           [35 / 384, 0, 500 / 1113, 125 / 192, -2187 / 6784, 11 / 84]]):
+    _DP_BETA[_i, :len(_row)] = torch.tensor(_row, dtype=torch.float64)
+_DP_CSOL = torch.tensor([35 / 384, 0, 500 / 1113, 125 / 192, -2187 / 6784, 11 / 84, 0], dtype=torch.float64)
+_DP_CERR = torch.tensor([35 / 384 - 1951 / 21600, 0, 500 / 1113 - 22642 / 50085, 125 / 192 - 451 / 720,
+                         -2187 / 6784 - -12231 / 42400, 11 / 84 - 649 / 6300, -1 / 60], dtype=torch.float64)
+_DP_CMID = torch.tensor([6025192743 / 30085553152 / 2, 0, 51252292925 / 65400821598 / 2,
+                         -2691868925 / 45128329728 / 2, 187940372067 / 1594534317056 / 2,
+                         -1776094331 / 19743644256 / 2, 11237099 / 235043384 / 2], dtype=torch.float64)
+
+
+def _dp_step(func, t0, dt, y0, f0):
+    """torchdiffeq _impl/rk_common.py:_runge_kutta_step on the Dormand-Prince-Shampine tableau: the stage
+    matrix k[..., i] is filled left to right, every stage state is y0 + k @ (beta_i * dt)."""
+    k = torch.zeros(*y0.shape, 7, dtype=y0.dtype, device=y0.device)
+    k[..., 0] = f0
+    yi = y0
+    for i in range(6):
+        yi = y0 + k @ (_DP_BETA[i] * dt).to(y0.dtype)
+        k[..., i + 1] = func(t0 + float(_DP_ALPHA[i]) * dt, yi)
+    y1 = yi                                             # c_sol[:-1] == beta[-1], c_sol[-1] == 0 (FSAL)
+    f1 = k[..., -1]
+    err = k @ (_DP_CERR * dt).to(y0.dtype)
+    y_mid = y0 + k @ (_DP_CMID * dt).to(y0.dtype)
+    return y1, f1, err, y_mid
+
+
+def _dp_interp(y0, y1, y_mid, f0, f1, dt, x):
+    """torchdiffeq _impl/interp.py: _interp_fit + _interp_evaluate at x = (t - t0) / dt."""
+    a = 2 * dt * (f1 - f0) - 8 * (y1 + y0) + 16 * y_mid
+    b = dt * (5 * f0 - 3 * f1) + 18 * y0 + 14 * y1 - 32 * y_mid
+    c = dt * (f1 - 4 * f0) - 11 * y0 - 5 * y1 + 16 * y_mid
+    d = dt * f0
+    return y0 + x * (d + x * (c + x * (b + x * a)))
+
+
+def _rms(x):
+    return float(x.abs().pow(2).mean().sqrt())         # torchdiffeq _impl/misc.py:_rms_norm
+
+
+def dopri5_solve(func, y0, t_end, rtol=1e-3, atol=1e-6, t_start=0.0):
+    """Adaptive solve from t_start to t_end (torchdiffeq _impl/rk_common.py:RKAdaptiveStepsizeODESolver:
+    _before_integrate, _advance, _adaptive_step; misc.py:_select_initial_step, _compute_error_ratio,
+    _optimal_step_size). Returns (y(t_end), accepted steps [(t0, dt)], nfe)."""
+    f0 = func(t_start, y0)
+    nfe = 1
+    scale = atol + y0.abs() * rtol                                                    # _select_initial_step, order = 4
+    d0, d1 = _rms(y0 / scale), _rms(f0 / scale)
+    h0 = 1e-6 if (d0 < 1e-5 or d1 < 1e-5) else 0.01 * d0 / d1
+    f_probe = func(t_start + h0, y0 + h0 * f0)
+    nfe += 1
+    d2 = _rms((f_probe - f0) / scale) / h0
+    h1 = max(1e-6, h0 * 1e-3) if (d1 <= 1e-15 and d2 <= 1e-15) else (0.01 / max(d1, d2)) ** (1.0 / 5.0)
+    dt = min(100 * h0, h1)
+    t, y, f = t_start, y0, f0
+    last = None
+    steps = []
+    while t_end > t:                                                                  # _advance: no clipping to t_end
+        y1, f1, err, y_mid = _dp_step(func, t, dt, y, f)
+        nfe += 6
+        ratio = _rms(err / (atol + rtol * torch.max(y.abs(), y1.abs())))              # _compute_error_ratio
+        if ratio <= 1:                                                                # accept
+            last = (t, dt, y, y1, y_mid, f, f1)
+            steps.append((t, dt))
+            t, y, f = t + dt, y1, f1
+        if ratio == 0:                                                                # _optimal_step_size
+            dt = dt * 10.0
+        else:
+            dt = dt * min(10.0, max(0.9 / ratio ** 0.2, 1.0 if ratio < 1 else 0.2))
+    t0, h, ya, yb, ym, fa, fb = last
+    return _dp_interp(ya, yb, ym, fa, fb, h, (t_end - t0) / h), steps, nfe
+
+
+def dopri5_replay(func, y0, steps, t_end):
+    """The same Dormand-Prince steps with a GIVEN accepted step sequence [(t0, dt)] (no controller) and the
+    dense output at t_end inside the last step: used to compare two right-hand sides (oracle vs CUDA forward)
+    without the accept/reject decisions amplifying rounding differences."""
+    y = y0
+    f = func(steps[0][0], y0)
+    last = None
+    for t0, dt in steps:
+        y1, f1, _, y_mid = _dp_step(func, t0, dt, y, f)
+        last = (t0, dt, y, y1, y_mid, f, f1)
+        y, f = y1, f1
+    t0, h, ya, yb, ym, fa, fb = last
+    return _dp_interp(ya, yb, ym, fa, fb, h, (t_end - t0) / h)
+
+
+def _rhs(sd, cfg, kw):
+    def func(t, x):
+        tv = torch.ones(x.shape[0], device=x.device) * float(t)                       # integrators.py:98-101
+        return forward(sd, cfg, x, tv, **kw)
+    return func
+
+
+def sample_dopri5(sd, cfg, zs, rtol=1e-3, atol=1e-6, **kw):
+    """Sampler.sample_ode('dopri5') (the reference's default sampling_method, mdgen/parsing.py:102): last state,
+    accepted steps and number of model evaluations."""
+    return dopri5_solve(_rhs(sd, cfg, kw), zs, 1.0, rtol=rtol, atol=atol)
+
+
+def sample_dopri5_replay(sd, cfg, zs, steps, **kw):
+    return dopri5_replay(_rhs(sd, cfg, kw), zs, steps, 1.0)
 
 
 # --------------------------------------------------------------------------- wrapper pieces

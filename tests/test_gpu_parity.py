@@ -135,6 +135,43 @@ def test_attention_variants_match_oracle(shape, variant):
     assert rel_l2(xk.cpu(), xo) < TOL
 
 
+def test_dopri5_sampler_matches_oracle_replay():
+    """the reference's default adaptive sampler (`--sampling_method dopri5`,
+    integrators.py:106-113 -> torchdiffeq) around the CUDA forward. The accepted step sequence of the GPU run is
+    replayed through the oracle (same Dormand-Prince steps and dense output, CPU forward), so only the two
+    right-hand sides differ; the oracle's own adaptive run must land on the same solution within the
+    integrator's tolerance (its accept / reject decisions may differ at rounding level)."""
+    from mdgen_b200.config import config_from_args, default_args
+    from oracle import mdgen_oracle as O
+    B, T, L = 2, 24, 4
+    args = default_args(sim_condition=True, prepend_ipa=True, crop=L, num_frames=T, abs_pos_emb=True,
+                        sampling_method="dopri5")
+    cfg = config_from_args(args)
+    sd = synthetic_state_dict(cfg, seed=0)
+    batch = synthetic_batch(B, T, L, seed=5)
+    zs = synthetic_noise(B, T, L, cfg.latent_dim, seed=6)
+    m = _wrapper(args, sd, "bf16")
+    prep = m.prep_batch(_dev(batch))
+    sample_fn = m.transport_sampler.sample_ode(sampling_method=args.sampling_method)   # == wrapper.py:441
+    x = sample_fn(zs.cuda(), m.model.forward_inference, **prep["model_kwargs"])[-1]
+    st = m.transport_sampler.last_stats
+    assert st["accepted"] >= 2 and st["nfe"] == 2 + 6 * (st["accepted"] + st["rejected"])
+    assert st["steps"][-1][0] < 1.0 <= st["steps"][-1][0] + st["steps"][-1][1]
+    op = O.prep_batch(cfg, batch)
+    kw = dict(mask=op["mask"], start=op["start"], end=op["end"], x_cond=op["x_cond"],
+              x_cond_mask=op["x_cond_mask"], aatype=op["aatype"])
+    with torch.no_grad():
+        xr = O.sample_dopri5_replay(sd, cfg, zs, st["steps"], **kw)
+        xa, steps, nfe = O.sample_dopri5(sd, cfg, zs, **kw)
+    assert max_rel(x.cpu(), xr) < TOL, max_rel(x.cpu(), xr)
+    assert rel_l2(x.cpu(), xa) < 5e-3, (rel_l2(x.cpu(), xa), len(steps), st["accepted"])
+    # public API: inference() with the default sampling_method decodes that state
+    atom14, _ = m.inference(_dev(batch), zs=zs.cuda())
+    a_ref = m.model.engine().decode_atom14(x, _dev(batch)["rots"][:, 0], _dev(batch)["trans"][:, 0],
+                                           _dev(batch)["seqres"])
+    assert torch.isfinite(atom14).all() and max_rel(atom14.cpu(), a_ref.cpu()) < 1e-6
+
+
 def test_no_cpu_fallback():
     """The product path must fail loudly on CPU tensors instead of silently falling back."""
     from mdgen_b200._lib import MDGenError
