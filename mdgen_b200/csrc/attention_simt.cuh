@@ -180,6 +180,81 @@ __global__ void __launch_bounds__(256) attn_l4_kernel(AttnParams p) {
                    make_float4(o[4*i] * inv, o[4*i+1] * inv, o[4*i+2] * inv, o[4*i+3] * inv), p.round_out);
 }
 
+// ---- S == 4, shared-memory exchange (experiment, option l4_variant = 1, pending hardware validation):
+// same lane mapping and the same arithmetic order as attn_l4_kernel (results are bit-identical), but the
+// rotated keys and the values of the four sibling tokens are exchanged through a warp-private shared-memory
+// tile (48 multicast 128-bit reads per lane) instead of 192 warp shuffles. Head stride padded to 28 floats:
+// the 8 heads of a multicast read fall into 8 distinct 4-bank groups.
+constexpr int L4_HS = 28;
+__global__ void __launch_bounds__(128) attn_l4s_kernel(AttnParams p) {
+  __shared__ __align__(16) float ks[4][4][8][L4_HS];
+  __shared__ __align__(16) float vs[4][4][8][L4_HS];
+  const SeqMap& sm = p.sm;
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long w = (long long)blockIdx.x * 4 + wib;        // warp = (sequence, head octet)
+  if (w >= sm.num_seq * 2) return;                            // whole warps leave; no block-wide barrier below
+  const long long s = w >> 1;
+  const int tl = lane >> 3, hh = lane & 7, h = (int)(w & 1) * 8 + hh;
+  const long long tok = seq_token(sm, s, tl);
+  float q[kHD], t[kHD];
+  load24(p.qkv, (size_t)tok * kQKV + h * kHD, p.qkv_bf16, q);
+  load24(p.qkv, (size_t)tok * kQKV + kC + h * kHD, p.qkv_bf16, t);
+  rope24(q, p.cosT + tl * kHalf, p.sinT + tl * kHalf);
+  rope24(t, p.cosT + tl * kHalf, p.sinT + tl * kHalf);
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+    *reinterpret_cast<float4*>(&ks[wib][tl][hh][4 * i]) = make_float4(t[4*i], t[4*i+1], t[4*i+2], t[4*i+3]);
+  load24(p.qkv, (size_t)tok * kQKV + 2 * kC + h * kHD, p.qkv_bf16, t);
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+    *reinterpret_cast<float4*>(&vs[wib][tl][hh][4 * i]) = make_float4(t[4*i], t[4*i+1], t[4*i+2], t[4*i+3]);
+  const bool valid = p.mask == nullptr || p.mask[tok] != 0.f;
+  const unsigned vmask = __ballot_sync(0xffffffffu, valid);   // bit 8 j = token j of this sequence is real
+  __syncwarp();
+  float sc[5];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float d = 0.f;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const float4 k4 = *reinterpret_cast<const float4*>(&ks[wib][j][hh][4 * i]);
+      d = fmaf(q[4*i], k4.x, d); d = fmaf(q[4*i+1], k4.y, d); d = fmaf(q[4*i+2], k4.z, d); d = fmaf(q[4*i+3], k4.w, d);
+    }
+    sc[j] = ((vmask >> (8 * j)) & 1u) ? d : -INFINITY;
+  }
+#pragma unroll
+  for (int i = 0; i < kHD; ++i) t[i] = p.bias_k[h * kHD + i];
+  rope24(t, p.cosT + 4 * kHalf, p.sinT + 4 * kHalf);
+  {
+    float d = 0.f;
+#pragma unroll
+    for (int i = 0; i < kHD; ++i) d = fmaf(q[i], t[i], d);
+    sc[4] = d;
+  }
+  float m = sc[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) m = fmaxf(m, sc[j]);
+  float l = 0.f;
+#pragma unroll
+  for (int j = 0; j < 5; ++j) { sc[j] = __expf(sc[j] - m); l += sc[j]; }
+  const float inv = 1.0f / l;
+  float o[kHD];
+#pragma unroll
+  for (int i = 0; i < kHD; ++i) o[i] = sc[4] * p.bias_v[h * kHD + i];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const float4 v4 = *reinterpret_cast<const float4*>(&vs[wib][j][hh][4 * i]);
+      o[4*i] = fmaf(sc[j], v4.x, o[4*i]); o[4*i+1] = fmaf(sc[j], v4.y, o[4*i+1]);
+      o[4*i+2] = fmaf(sc[j], v4.z, o[4*i+2]); o[4*i+3] = fmaf(sc[j], v4.w, o[4*i+3]);
+    }
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+    store_operand4(p.out, (size_t)tok * kC + h * kHD + 4 * i,
+                   make_float4(o[4*i] * inv, o[4*i+1] * inv, o[4*i+2] * inv, o[4*i+3] * inv), p.round_out);
+}
+
 // ---- long sequences: block = (query tile of 256, head, sequence); 128 threads x 2 queries each;
 // K/V tiles of 32 keys staged (and rotated) in shared memory and broadcast to all threads.
 constexpr int AF_QT = 256;   // queries per block

@@ -315,7 +315,11 @@ __global__ void __launch_bounds__(256) attn_prep2_kernel(AttnParams p, uint8_t* 
 
 // PV16: P and V^T in bf16, P·V on kind::f16 (6 MMAs per key tile instead of 12, half the P stores); the
 //       default. PV16 = false keeps P and V in TF32 (kind::tf32) as the higher-precision reference variant.
-template <bool PV16>
+// BREF: experiment (not validated on hardware yet, off by default): a row that has no softmax reference yet adopts
+//       the Cauchy-Schwarz bound |q_i| max_j |k_j| of its first key tile as reference (when that bound is small
+//       enough that nothing can underflow) instead of the exact row maximum, which removes the second TMEM read of
+//       the first key tile and the row-max exchange between the two column-half warps.
+template <bool PV16, bool BREF>
 __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(AttnParams p, const uint8_t* __restrict__ scratch) {
   constexpr int IMG = at_img_bytes(PV16);
   constexpr int VT = at_vt_bytes(PV16);
@@ -472,8 +476,10 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(AttnParams p, co
       const float bound = qn * fmaxf(kn.x, fmaxf(kn.y, kn.z));          // >= every score of this row & tile
       // exact two-pass only when this row has no reference yet or the bound could overflow exp2
       // (identical decision in both warps of a row pair: same m_run, same bound)
-      const bool need_exact = __any_sync(0xffffffffu, (m_run == -INFINITY) || (bound - m_run > 100.f));
-      float m_new = m_run;
+      const bool fresh = m_run == -INFINITY;
+      const bool adopt = BREF && fresh && bound <= 40.f;      // same decision in both warps of a row
+      const bool need_exact = __any_sync(0xffffffffu, (fresh && !adopt) || (!fresh && bound - m_run > 100.f));
+      float m_new = (adopt && !need_exact) ? bound : m_run;
       if (need_exact) {
         // ---- pass 1: exact row max over this warp's columns, then exchange with the partner warp
         float tmax = -INFINITY;
@@ -993,11 +999,11 @@ inline size_t attn_tc_scratch_bytes(const SeqMap& sm) {
   return (size_t)sm.num_seq * kH * nkt * at_img_bytes(false);
 }
 
-template <bool PV16>
+template <bool PV16, bool BREF>
 inline int attn_tc_launch_t(const AttnParams& p, uint8_t* scratch, int prep2, bool prep_only, cudaStream_t s, std::string* err) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<PV16>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<PV16, BREF>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(attn_prep2_kernel<PV16>, cudaFuncAttributeMaxDynamicSharedMemorySize, AP2_SMEM_BYTES);
     if (e != cudaSuccess) {
@@ -1014,7 +1020,7 @@ inline int attn_tc_launch_t(const AttnParams& p, uint8_t* scratch, int prep2, bo
   else
     attn_prep_kernel<PV16><<<(unsigned)blocks, 256, 0, s>>>(p, scratch);
   if (!prep_only)
-    attn_tc_kernel<PV16><<<(unsigned)(blocks * nqt), AT_THREADS, AT_SMEM_BYTES, s>>>(p, scratch);
+    attn_tc_kernel<PV16, BREF><<<(unsigned)(blocks * nqt), AT_THREADS, AT_SMEM_BYTES, s>>>(p, scratch);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     if (err) *err = std::string("attn_tc launch: ") + cudaGetErrorString(e);
@@ -1026,6 +1032,7 @@ inline int attn_tc_launch_t(const AttnParams& p, uint8_t* scratch, int prep2, bo
 // `variant` (option attn_variant) selects the build variant of the tcgen05 attention:
 //   bit 0 (1)  : bf16 P·V (PV16)                         bit 1 (2) : staged pre-pass (attn_prep2_kernel)
 //   bit 2 (4)  : persistent kernel (implies PV16)        bit 3 (8) : ... with 12 instead of 8 softmax warps
+//   bit 7 (128): bound-adopted first softmax reference (BREF, experiment pending hardware validation)
 //   timing experiments, results undefined: bit 4 (16) pre-pass only; bits 5-6 DBG mode of the persistent kernel
 // Default 3. Measured on B200 at B=64, T=1000, L=4 (profiles/r1_attention_ncu.md): 0 -> 2.20 ms per mha_t
 // launch, 1 -> 2.05, 3 -> 1.95, 7 -> 1.96-2.05, 15 -> 2.08.
@@ -1034,8 +1041,11 @@ inline int attn_tc_launch(const AttnParams& p, uint8_t* scratch, int variant, cu
   const int p2 = (variant >> 1) & 1;
   const bool po = (variant & 16) != 0;
   if (variant & 4) return attn_tcp_launch(p, scratch, p2, ((variant >> 5) & 3) | ((variant & 8) ? 4 : 0), s, err);
-  return (variant & 1) ? attn_tc_launch_t<true>(p, scratch, p2, po, s, err)
-                       : attn_tc_launch_t<false>(p, scratch, p2, po, s, err);
+  if (variant & 128)   // experiment: bound-adopted softmax reference (BREF)
+    return (variant & 1) ? attn_tc_launch_t<true, true>(p, scratch, p2, po, s, err)
+                         : attn_tc_launch_t<false, true>(p, scratch, p2, po, s, err);
+  return (variant & 1) ? attn_tc_launch_t<true, false>(p, scratch, p2, po, s, err)
+                       : attn_tc_launch_t<false, false>(p, scratch, p2, po, s, err);
 }
 
 }  // namespace mdgen

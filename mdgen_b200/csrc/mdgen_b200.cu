@@ -79,6 +79,7 @@ struct mdgen_handle {
   int64_t graph_launches_per_pair = 0, graph_replays = 0;
   bool trunk_precomputed = false;   // set by mdgen_sample_euler while the step loop runs
   int use_tc_attn = 1; // tcgen05 attention for sequences longer than 64 (needs use_tc)
+  int l4_variant = 0;   // S = 4 residue attention: 1 = shared-memory exchange kernel (experiment, see attention_simt.cuh)
 #ifdef MDGEN_NO_TC
   int attn_variant = 0;
 #else
@@ -401,7 +402,8 @@ int attention(mdgen_handle* h, cudaStream_t s, const float* qkv, const float* ma
 #endif
   if (sm.S == 4) {
     long long threads = sm.num_seq * 2 * 32;
-    attn_l4_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(p);
+    if (h->l4_variant) attn_l4s_kernel<<<(unsigned)((sm.num_seq * 2 + 3) / 4), 128, 0, s>>>(p);
+    else attn_l4_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(p);
   } else if (sm.S <= 64) {
     long long total = sm.num_seq * sm.S * kH;
     attn_small_kernel<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(p);
@@ -1020,7 +1022,8 @@ int mdgen_set_option(mdgen_handle* h, const char* key, int64_t value) {
     h->use_tc = (int)value;
   } else if (k == "tc_min_rows") h->tc_min_rows = (int)value;
   else if (k == "use_tc_attn") h->use_tc_attn = (int)value;
-  else if (k == "attn_variant") h->attn_variant = (int)value & 127;
+  else if (k == "attn_variant") h->attn_variant = (int)value & 255;
+  else if (k == "l4_variant") h->l4_variant = (int)value & 1;
   else if (k == "emu_bf16") h->emu_bf16 = (int)value;
   else if (k == "gemm_bf16") h->gemm_bf16 = (int)value;
   else if (k == "use_graph") h->use_graph = (int)value;
@@ -1042,6 +1045,7 @@ int64_t mdgen_get_option(const mdgen_handle* h, const char* key) {
   if (k == "tc_min_rows") return h->tc_min_rows;
   if (k == "use_tc_attn") return h->use_tc_attn;
   if (k == "attn_variant") return h->attn_variant;
+  if (k == "l4_variant") return h->l4_variant;
   if (k == "gemm_bf16") return h->gemm_bf16;
   if (k == "use_graph") return h->use_graph;
   if (k == "graph_replays") return h->graph_replays;

@@ -9,7 +9,9 @@ from the exact-fp32 SIMT path of the same library. Prints one JSON line per vari
 
 Variant bits: 1 bf16 P.V, 2 staged pre-pass, 4 persistent kernel, 8 persistent with 12 softmax warps, 16 pre-pass
 only (timing aid, output undefined), 32/64/96 debug modes of the persistent kernel (no MUFU / no P.V MMAs / no TMEM
-traffic in the probability loop; output undefined).
+traffic in the probability loop; output undefined), 128 bound-adopted first softmax reference (experiment).
+`--l4 1` switches the S = 4 residue attention to the shared-memory exchange kernel (must be bit-identical:
+rel_vs_variant0 == 0 when run with the same attn_variant).
 """
 import argparse
 import json
@@ -21,7 +23,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--variants", default="0,1,3,6,14,19")
+    ap.add_argument("--variants", default="0,1,3,131,6,14,19")
+    ap.add_argument("--l4", type=int, default=0, help="l4_variant (1 = shared-memory exchange kernel for S = 4)")
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--frames", type=int, default=1000)
     ap.add_argument("--residues", type=int, default=4)
@@ -65,6 +68,7 @@ def main():
         rec = {"variant": v}
         try:
             eng.set_option("attn_variant", v)
+            eng.set_option("l4_variant", a.l4)
             out1 = m.model.sample_euler(zs1, grid, **kw1)
             rec["rel_vs_fp32_simt_B1"] = rel(out1, ref1)
             out = m.model.sample_euler(zsB, grid, **kwB)       # warm-up + result
@@ -92,6 +96,7 @@ def main():
             rec["error"] = repr(ex)[:300]
         print(json.dumps(rec), flush=True)
     eng.set_option("attn_variant", 3)
+    eng.set_option("l4_variant", 0)
 
 
 if __name__ == "__main__":
