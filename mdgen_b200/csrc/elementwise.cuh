@@ -151,12 +151,16 @@ __global__ void __launch_bounds__(kC) embed_kernel(
   float bsum = (MODE == 0) ? (bias0[c] + bias1[c]) : 0.f;
   if (MODE == 1 && step_ptr) ipa += (size_t)(*step_ptr) * ipa_step_stride;   // trunk output of this Euler step
   __syncthreads();
-  // sample index / residue index of the block's first token; per-token values follow incrementally
-  // (a 64-bit division per token and thread used to dominate this kernel)
+  // sample index b / position inside the sample / residue index l of the block's first token; the values of
+  // the following tokens are stepped incrementally (per-token divisions and 64-bit index arithmetic used to
+  // cost ~3x the useful FMA work of this kernel)
   const long long TL = (long long)T * L;
-  long long b0 = n0 / TL;
-  long long rem0 = n0 - b0 * TL;
-  const int l0 = (int)(n0 % L);
+  long long b = n0 / TL;
+  long long rem = n0 - b * TL;
+  int l = (int)(rem % L);
+  const float* cond_p = (MODE == 1) ? cond + (size_t)n0 * kC + c : nullptr;
+  const float* ipa_b = (MODE == 1) ? ipa + (size_t)b * L * kC + c : nullptr;    // trunk rows of sample b
+  float* out_p = out + (size_t)n0 * kC + c;
   constexpr int U = 4;                 // tokens in flight per thread (independent global loads)
   for (int i = 0; i < nt; i += U) {
     float add[U];
@@ -164,16 +168,14 @@ __global__ void __launch_bounds__(kC) embed_kernel(
     for (int u = 0; u < U; ++u) {
       add[u] = 0.f;
       if (i + u < nt) {
-        const long long n = n0 + i + u;
-        const int l = (l0 + i + u) % L;
         if (MODE == 0) {
           add[u] = bsum + emask[(size_t)ms[i + u] * kC + c];
           if (pos) add[u] += pos[(size_t)l * kC + c];
         } else {
-          long long b = b0, rem = rem0 + i + u;
-          while (rem >= TL) { rem -= TL; ++b; }
-          add[u] = cond[(size_t)n * kC + c] + ipa[((size_t)b * L + l) * kC + c];
+          add[u] = cond_p[(size_t)(i + u) * kC] + ipa_b[(size_t)l * kC];
         }
+        if (++l == L) l = 0;                                   // step to the next token
+        if (++rem == TL) { rem = 0; ++b; if (MODE == 1) ipa_b = ipa + (size_t)b * L * kC + c; }
       }
     }
 #pragma unroll
@@ -186,7 +188,7 @@ __global__ void __launch_bounds__(kC) embed_kernel(
           s = fmaf(w[4 * k4], xv.x, s); s = fmaf(w[4 * k4 + 1], xv.y, s);
           s = fmaf(w[4 * k4 + 2], xv.z, s); s = fmaf(w[4 * k4 + 3], xv.w, s);
         }
-        out[(size_t)(n0 + i + u) * kC + c] = s + add[u];
+        out_p[(size_t)(i + u) * kC] = s + add[u];
       }
     }
   }
