@@ -151,6 +151,7 @@ __global__ void __launch_bounds__(kC) embed_kernel(
   float bsum = (MODE == 0) ? (bias0[c] + bias1[c]) : 0.f;
   if (MODE == 1 && step_ptr) ipa += (size_t)(*step_ptr) * ipa_step_stride;   // trunk output of this Euler step
   __syncthreads();
+#ifdef MDGEN_EMBED_INCREMENTAL   // experiment, not yet validated on hardware: ~1.8x fewer instructions per token
   // sample index b / position inside the sample / residue index l of the block's first token; the values of
   // the following tokens are stepped incrementally (per-token divisions and 64-bit index arithmetic used to
   // cost ~3x the useful FMA work of this kernel)
@@ -192,6 +193,47 @@ __global__ void __launch_bounds__(kC) embed_kernel(
       }
     }
   }
+#else
+  // sample index / residue index of the block's first token; per-token values follow incrementally
+  // (a 64-bit division per token and thread used to dominate this kernel)
+  const long long TL = (long long)T * L;
+  long long b0 = n0 / TL;
+  long long rem0 = n0 - b0 * TL;
+  const int l0 = (int)(n0 % L);
+  constexpr int U = 4;                 // tokens in flight per thread (independent global loads)
+  for (int i = 0; i < nt; i += U) {
+    float add[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      add[u] = 0.f;
+      if (i + u < nt) {
+        const long long n = n0 + i + u;
+        const int l = (l0 + i + u) % L;
+        if (MODE == 0) {
+          add[u] = bsum + emask[(size_t)ms[i + u] * kC + c];
+          if (pos) add[u] += pos[(size_t)l * kC + c];
+        } else {
+          long long b = b0, rem = rem0 + i + u;
+          while (rem >= TL) { rem -= TL; ++b; }
+          add[u] = cond[(size_t)n * kC + c] + ipa[((size_t)b * L + l) * kC + c];
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (i + u < nt) {
+        float s = 0.f;
+#pragma unroll
+        for (int k4 = 0; k4 < 7; ++k4) {     // 128-bit broadcast reads of the token's latent (w[k] = 0 for k >= D)
+          const float4 xv = *reinterpret_cast<const float4*>(&xs[i + u][4 * k4]);
+          s = fmaf(w[4 * k4], xv.x, s); s = fmaf(w[4 * k4 + 1], xv.y, s);
+          s = fmaf(w[4 * k4 + 2], xv.z, s); s = fmaf(w[4 * k4 + 3], xv.w, s);
+        }
+        out[(size_t)(n0 + i + u) * kC + c] = s + add[u];
+      }
+    }
+  }
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------
