@@ -169,7 +169,7 @@ def test_dopri5_sampler_matches_oracle_replay():
     atom14, _ = m.inference(_dev(batch), zs=zs.cuda())
     a_ref = m.model.engine().decode_atom14(x, _dev(batch)["rots"][:, 0], _dev(batch)["trans"][:, 0],
                                            _dev(batch)["seqres"])
-    assert torch.isfinite(atom14).all() and max_rel(atom14.cpu(), a_ref.cpu()) < 1e-6
+    assert torch.isfinite(atom14).all() and rel_l2(atom14.cpu(), a_ref.cpu()) < 1e-4
 
 
 def test_no_cpu_fallback():
