@@ -144,7 +144,18 @@ int mdgen_featurize_atom14(mdgen_handle* h, int32_t B, int32_t L, const float* a
 int mdgen_abi_version(void);
 /* number of kernel launches issued by this handle since creation (bench.py's gpu_launches) */
 int64_t mdgen_launch_count(const mdgen_handle* h);
-/* 0 = SIMT fp32 validation kernels, 1 = tcgen05 TF32 tensor-core kernels (default when built) */
+/* Tuning / validation knobs (none of them is needed for normal use; the defaults are the measured-best path):
+ *   "use_tc"        1 (default) tcgen05 tensor-core GEMMs and attention, 0 = exact-fp32 SIMT validation kernels
+ *   "gemm_bf16"     1 (default) bf16 operands (kind::f16) for the token GEMMs, 0 = TF32 operands (kind::tf32)
+ *   "use_tc_attn"   1 (default) tcgen05 fused attention for sequences longer than 64
+ *   "attn_variant"  build variant of that attention (default 3: bf16 P.V + staged pre-pass; bit 2 persistent
+ *                   kernel, bit 3 with 12 softmax warps, bit 7 bound-adopted softmax reference; bits 4-6 are timing
+ *                   aids whose output is undefined - see csrc/attention_tc.cuh)
+ *   "l4_variant"    0 (default) shuffle-based S = 4 residue attention, 1 = shared-memory exchange kernel
+ *   "tc_min_rows"   GEMMs with fewer rows (the IPA key-frame trunk) stay on the exact-fp32 skinny GEMM (1024)
+ *   "use_graph", "graph_max_tokens"   CUDA-graph replay of the Euler steps for launch-bound workloads (1, 65536)
+ *   "emu_bf16"      precision experiments (tools/diag_precision.py);  "profile" 1 = per-family CUDA-event timing
+ * Unknown keys return MDGEN_E_INVALID. */
 int mdgen_set_option(mdgen_handle* h, const char* key, int64_t value);
 int64_t mdgen_get_option(const mdgen_handle* h, const char* key);
 /* Accumulated device time (ms) per kernel family since the last reset; fills up to `cap`
