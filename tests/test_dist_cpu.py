@@ -52,3 +52,29 @@ def test_two_rank_gloo_sharding_and_max_time():
     assert (a0, b0, a1, b1) == (0, 33, 33, 65)
     assert s0 == s1 == 15.0                     # max over ranks, identical on both
     assert c0 == c1 == [33, 32]
+
+
+def test_reference_arm_under_torchrun_prints_one_line():
+    """bench.py --impl reference launched the way the driver launches it for N > 1: rank 0 alone runs the CPU
+    port on a bounded sample and prints ONE JSON line with the contract's keys; the other rank exits 0 silently."""
+    import json
+    import os
+    import socket
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), "bench.py", "--impl", "reference",
+           "--gpus", "2", "--steps", "1", "--warmup", "0", "--frames", "24", "--euler-steps", "4"]
+    r = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, r.stdout[-2000:]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["unit"] == "frames/s" and d["value"] > 0
+    assert d["higher_is_better"] is True and d["gpu_launches"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
