@@ -393,7 +393,7 @@ def main():
                        "no data-path collective)", "l2": "working set (>4 GB activations per forward) "
                        "far exceeds the 126 MB L2; no explicit flush needed",
                        "graph_replays": eng.get_option("graph_replays"),
-                       "gemm_path": ("tcgen05 " + ("bf16 operands (token GEMMs) / TF32 (attention), fp32 accumulate; "
+                       "gemm_path": ("tcgen05 " + ("bf16 operands (token GEMMs, attention P.V) / TF32 (attention Q.K^T), fp32 accumulate; "
                                      "IPA key-frame trunk fp32" if eng.get_option("gemm_bf16") else "TF32"))
                                     if use_tc else "fp32 SIMT"},
             "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
