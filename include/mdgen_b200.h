@@ -16,9 +16,10 @@
  *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream). Calls enqueue work on
  *     it and return without synchronising the device (workspace growth may call cudaMalloc).
  *   - one handle per (device, stream); a handle is not thread-safe across concurrent calls.
- *   - all floating point is fp32 at the boundary. Internally the dense contractions run on the
- *     tensor cores with TF32 operands and fp32 accumulation; softmax, LayerNorm statistics, the
- *     residual stream and the Euler state stay fp32.
+ *   - all floating point is fp32 at the boundary. Internally the token GEMMs run on the tensor cores
+ *     with bf16 operands (option "gemm_bf16" = 0: TF32 operands), the attention contractions with
+ *     fp16 / bf16 operands, all with fp32 accumulation; the IPA key-frame trunk, softmax
+ *     denominators, LayerNorm statistics, the residual stream and the Euler state stay fp32.
  */
 #ifndef MDGEN_B200_H_
 #define MDGEN_B200_H_
@@ -29,7 +30,7 @@
 extern "C" {
 #endif
 
-#define MDGEN_ABI_VERSION 1
+#define MDGEN_ABI_VERSION 2
 
 enum {
   MDGEN_OK = 0,
@@ -71,6 +72,12 @@ typedef struct mdgen_cond {
   const float* x_cond;        /* [B,T,L,latent_dim]                                   */
   const int64_t* x_cond_mask; /* [B,T,L]   0/1                                        */
   const int64_t* aatype;      /* [B,L]     0..20                                      */
+  /* Two-trunk configs only, optional (NULL = canonical w >= 0): sign (+1 / -1) applied to the relative
+   * quaternions fed to latent_to_emb_r ([0,:,:] = end^-1 o start) and latent_to_emb_f ([1,:,:] =
+   * start^-1 o end). The reference keeps whatever sign torch.linalg.eigh returns there
+   * (mdgen/model/latent_model.py:194-195 -> mdgen/rigid_utils.py:191-210); a caller that must
+   * reproduce it bit-for-sign passes sign(eigh(...)[..., -1][..., 0]) computed on its own backend. */
+  const float* quat_sign;     /* [2,B,L]   or NULL                                    */
 } mdgen_cond;
 
 /* Lifetime. Replaces LatentMDGenModel.__init__ (mdgen/model/latent_model.py:44-128). */

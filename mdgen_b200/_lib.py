@@ -39,7 +39,7 @@ class CConfig(C.Structure):
 class CCond(C.Structure):
     _fields_ = [("B", C.c_int32), ("T", C.c_int32), ("L", C.c_int32)] + [
         (n, C.c_void_p) for n in ("mask", "start_rot", "start_trans", "end_rot", "end_trans",
-                                  "x_cond", "x_cond_mask", "aatype")]
+                                  "x_cond", "x_cond_mask", "aatype", "quat_sign")]
 
 
 def lib_path() -> str:
@@ -108,7 +108,7 @@ class Engine:
         self.lib = load_library()
         self.cfg = cfg
         cc = CConfig(
-            abi_version=1, latent_dim=cfg.latent_dim, num_layers=cfg.num_layers, crop=cfg.crop,
+            abi_version=2, latent_dim=cfg.latent_dim, num_layers=cfg.num_layers, crop=cfg.crop,
             abs_pos_emb=int(cfg.abs_pos_emb), use_aa_emb=int(cfg.use_aa_emb),
             sim_condition=int(cfg.sim_condition), tps_condition=int(cfg.tps_condition),
             inpainting=int(cfg.inpainting), cond_interval=int(cfg.cond_interval),
@@ -188,7 +188,7 @@ class Engine:
         return out
 
     # -- calls -------------------------------------------------------------------------------
-    def _cond(self, B, T, L, mask, start, end, x_cond, x_cond_mask, aatype):
+    def _cond(self, B, T, L, mask, start, end, x_cond, x_cond_mask, aatype, quat_sign=None):
         keep = {}
         keep["mask"] = _f32(mask.expand(B, T, L) if mask.dim() == 3 else mask, "mask")
         keep["start_rot"] = _f32(start[0], "start_rot")
@@ -200,6 +200,9 @@ class Engine:
         keep["x_cond_mask"] = _i64(x_cond_mask, "x_cond_mask")
         if aatype is not None:
             keep["aatype"] = _i64(aatype, "aatype")
+        if quat_sign is not None:
+            keep["quat_sign"] = _f32(quat_sign, "quat_sign")
+            assert keep["quat_sign"].shape == (2, B, L)
         D = self.cfg.latent_dim
         assert keep["mask"].shape == (B, T, L)
         assert keep["start_rot"].shape == (B, L, 3, 3) and keep["start_trans"].shape == (B, L, 3)
@@ -209,23 +212,23 @@ class Engine:
             setattr(c, k, v.data_ptr())
         return c, keep
 
-    def forward(self, x, t, mask, start, end, x_cond, x_cond_mask, aatype):
+    def forward(self, x, t, mask, start, end, x_cond, x_cond_mask, aatype, quat_sign=None):
         B, T, L, D = x.shape
         x = _f32(x, "x")
         t = _f32(t, "t").reshape(B)
-        c, keep = self._cond(B, T, L, mask, start, end, x_cond, x_cond_mask, aatype)
+        c, keep = self._cond(B, T, L, mask, start, end, x_cond, x_cond_mask, aatype, quat_sign)
         out = torch.empty_like(x)
         self._check(self.lib.mdgen_forward(self.h, x.data_ptr(), t.data_ptr(), C.byref(c),
                                            out.data_ptr(), _stream()))
         return out
 
-    def sample_euler(self, zs, t_grid, mask, start, end, x_cond, x_cond_mask, aatype):
+    def sample_euler(self, zs, t_grid, mask, start, end, x_cond, x_cond_mask, aatype, quat_sign=None):
         B, T, L, D = zs.shape
         zs = _f32(zs, "zs")
         tg = np.ascontiguousarray(t_grid.detach().cpu().numpy() if torch.is_tensor(t_grid)
                                   else np.asarray(t_grid), np.float32)
         K = int(tg.shape[0]) - 1
-        c, keep = self._cond(B, T, L, mask, start, end, x_cond, x_cond_mask, aatype)
+        c, keep = self._cond(B, T, L, mask, start, end, x_cond, x_cond_mask, aatype, quat_sign)
         out = torch.empty_like(zs)
         self._check(self.lib.mdgen_sample_euler(self.h, zs.data_ptr(), tg.ctypes.data, K, C.byref(c),
                                                 out.data_ptr(), _stream()))

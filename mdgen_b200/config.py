@@ -92,6 +92,7 @@ class MDGenConfig:
 UNSUPPORTED_FLAGS = (
     "design", "hyena", "no_rope", "interleave_ipa", "abs_time_emb", "dynamic_mpnn", "mpnn",
     "no_frames", "no_offsets", "design_key_frames",
+    "oracle",          # skips the torsion normalisation of inference() (wrapper.py:474-476); decode_kernel normalises
 )
 
 

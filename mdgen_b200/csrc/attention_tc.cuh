@@ -944,27 +944,27 @@ __global__ void __launch_bounds__(atp_threads(NP), 2) attn_tcp_kernel(AttnParams
 
 template <int DBG, int NP>
 inline void attn_tcp_kernel_launch(const AttnParams& p, const uint8_t* scratch, int items, int grid, cudaStream_t s) {
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {false};
+  const int dev = current_device();
+  if (!configured[dev]) {
     cudaFuncSetAttribute(attn_tcp_kernel<DBG, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATP_SMEM_BYTES);
-    configured = true;
+    configured[dev] = true;
   }
   attn_tcp_kernel<DBG, NP><<<grid, atp_threads(NP), ATP_SMEM_BYTES, s>>>(p, scratch, items);
 }
 
 // mode: bits 0-1 = DBG, bit 2 = 12 softmax warps (NP = 3)
 inline int attn_tcp_launch(const AttnParams& p, uint8_t* scratch, int prep2, int mode, cudaStream_t s, std::string* err) {
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_prep2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AP2_SMEM_BYTES);
-    if (e != cudaSuccess) {
-      num_sms = 0;
+  static bool configured[kMaxDevices] = {false};
+  const int dev = current_device();
+  const int num_sms = device_sm_count();
+  if (!configured[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(attn_prep2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AP2_SMEM_BYTES);
+    if (e != cudaSuccess || num_sms <= 0) {
       if (err) *err = std::string("attn_tcp setup: ") + cudaGetErrorString(e);
       return -2;
     }
+    configured[dev] = true;
   }
   const int nqt = (p.sm.S + AT_QT - 1) / AT_QT;
   const int nkt = (p.sm.S + 1 + AT_KT - 1) / AT_KT;
@@ -1001,8 +1001,9 @@ inline size_t attn_tc_scratch_bytes(const SeqMap& sm) {
 
 template <bool PV16, bool BREF>
 inline int attn_tc_launch_t(const AttnParams& p, uint8_t* scratch, int prep2, bool prep_only, cudaStream_t s, std::string* err) {
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {false};
+  const int dev = current_device();
+  if (!configured[dev]) {
     cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<PV16, BREF>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(attn_prep2_kernel<PV16>, cudaFuncAttributeMaxDynamicSharedMemorySize, AP2_SMEM_BYTES);
@@ -1010,7 +1011,7 @@ inline int attn_tc_launch_t(const AttnParams& p, uint8_t* scratch, int prep2, bo
       if (err) *err = std::string("cudaFuncSetAttribute(attn_tc): ") + cudaGetErrorString(e);
       return -2;
     }
-    configured = true;
+    configured[dev] = true;
   }
   const int nqt = (p.sm.S + AT_QT - 1) / AT_QT;
   const int nkt = (p.sm.S + 1 + AT_KT - 1) / AT_KT;

@@ -20,6 +20,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -386,6 +387,20 @@ __global__ void __launch_bounds__(128 + 32 * tc_epi_warps(MODE), 1) gemm_tc_kern
 }
 
 // ---- host side -------------------------------------------------------------------------------
+// Launch attributes (cudaFuncSetAttribute) and the SM count are per device: a process may own
+// handles on several GPUs, so the "already configured" state is kept per device ordinal.
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return (d >= 0 && d < kMaxDevices) ? d : 0;
+}
+inline int device_sm_count() {
+  static int n[kMaxDevices] = {0};
+  const int d = current_device();
+  if (!n[d]) cudaDeviceGetAttribute(&n[d], cudaDevAttrMultiProcessorCount, d);
+  return n[d];
+}
 inline bool tc_gemm_supported(int N, int K, bool bf16 = false) {
   const int bk = bf16 ? 64 : TC_BK;
   return (N % TC_BN == 0) && (K % bk == 0) && K >= bk;
@@ -437,6 +452,8 @@ struct TmapCacheEntry {
 inline int get_tmap(const void* ptr, long long rows, int cols, int ld, int box_rows, bool bf16, CUtensorMap* out,
                     std::string* err) {
   static std::vector<TmapCacheEntry> cache;
+  static std::mutex mu;                      // handles on different host threads share this cache
+  std::lock_guard<std::mutex> lock(mu);
   for (auto& e : cache)
     if (e.ptr == ptr && e.rows == rows && e.cols == cols && e.ld == ld && e.box_rows == box_rows &&
         e.bf16 == bf16) {
@@ -455,15 +472,16 @@ inline int get_tmap(const void* ptr, long long rows, int cols, int ld, int box_r
 template <int MODE, bool BF16IN, bool BF16OUT>
 inline int tc_launch_mode(const CUtensorMap& ta, const CUtensorMap& tb, long long M, int N, int K,
                           const Epilogue& ep, cudaStream_t s, int grid, std::string* err) {
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {false};
+  const int dev = current_device();
+  if (!configured[dev]) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<MODE, BF16IN, BF16OUT>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
     if (e != cudaSuccess) {
       if (err) *err = std::string("cudaFuncSetAttribute(gemm_tc): ") + cudaGetErrorString(e);
       return -2;
     }
-    configured = true;
+    configured[dev] = true;
   }
   gemm_tc_kernel<MODE, BF16IN, BF16OUT><<<grid, 128 + 32 * tc_epi_warps(MODE), TC_SMEM_BYTES, s>>>(ta, tb, M, N, K, ep);
   cudaError_t e = cudaGetLastError();
@@ -478,12 +496,7 @@ inline int tc_launch_mode(const CUtensorMap& ta, const CUtensorMap& tb, long lon
 inline int tc_gemm_launch(int mode, const void* A, int lda, const void* W, int ldw, long long M, int N, int K,
                           const Epilogue& ep, cudaStream_t s, std::string* err, bool in_bf16 = false,
                           bool out_bf16 = false) {
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-  }
+  const int num_sms = device_sm_count();
   CUtensorMap ta, tb;
   if (get_tmap(A, M, K, lda, TC_BM, in_bf16, &ta, err)) return -2;
   if (get_tmap(W, N, K, ldw, TC_BN, in_bf16, &tb, err)) return -2;

@@ -178,7 +178,8 @@ __global__ void __launch_bounds__(kC) ipa_init_kernel(
     const float* __restrict__ Wf, const float* __restrict__ bf, const float* __restrict__ Wr,
     const float* __restrict__ br, const float* __restrict__ mask /*[B,T,L]*/, int T, int L,
     float* __restrict__ x, float* __restrict__ frot, float* __restrict__ ftrans,
-    float* __restrict__ fmask /*[rows] = mask[:,0]*/, long long BL) {
+    float* __restrict__ fmask /*[rows] = mask[:,0]*/, long long BL,
+    const float* __restrict__ quat_sign /*[2,BL] or null: eigh's eigenvector sign (latent_model.py:194-195)*/) {
   __shared__ float o7[7];
   // rows are stacked as [replica (Euler step)][trunk (1 or 2)][B*L]
   long long row = blockIdx.x;
@@ -197,6 +198,7 @@ __global__ void __launch_bounds__(kC) ipa_init_kernel(
       const float* Ra = which == 0 ? erot + bl * 9 : srot + bl * 9;
       const float* ta = which == 0 ? etrans + bl * 3 : strans + bl * 3;
       relative_tensor7(Ra, ta, Rme, tme, o7);
+      if (quat_sign && quat_sign[which * BL + bl] < 0.f) { o7[0] = -o7[0]; o7[1] = -o7[1]; o7[2] = -o7[2]; o7[3] = -o7[3]; }
     }
     __syncthreads();
     const float* W = which == 0 ? Wr : Wf;

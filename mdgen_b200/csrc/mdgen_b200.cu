@@ -63,6 +63,8 @@ struct mdgen_handle {
   std::string err;
   std::map<std::string, RawTensor> raw;
   std::vector<void*> allocs;  // everything cudaMalloc'ed by the handle
+  std::vector<void*> weight_allocs;   // the subset holding packed weights (freed when weights are re-finalised)
+  bool alloc_is_weight = false;
   bool finalized = false;
   int64_t launches = 0;
 #ifdef MDGEN_NO_TC
@@ -110,6 +112,7 @@ struct mdgen_handle {
 
   // workspace
   long long cap_tokens = 0, cap_rows = 0;
+  long long cap_op_bytes = 0;   // (tokens + 128) x element size the GEMM-operand activation buffers hold (2 = bf16, 4 = fp32 / TF32)
   int cap_modrows = 0;
   float *h = nullptr, *xn = nullptr, *qkv = nullptr, *att = nullptr, *hid = nullptr, *cond = nullptr;
   float *xi = nullptr, *xni = nullptr, *proj = nullptr, *cat = nullptr, *qkvi = nullptr, *atti = nullptr,
@@ -176,6 +179,7 @@ int dev_alloc(mdgen_handle* h, void** p, size_t bytes) {
     return MDGEN_E_NOMEM;
   }
   h->allocs.push_back(*p);
+  if (h->alloc_is_weight) h->weight_allocs.push_back(*p);
   return MDGEN_OK;
 }
 template <typename T>
@@ -277,20 +281,31 @@ int ensure_rope(mdgen_handle* h, cudaStream_t s, int n) {
 }
 
 int ensure_workspace(mdgen_handle* h, long long N, long long rows, int modrows) {
+  // the GEMM-operand activations (xn, q|k|v, att, hid) are bf16 on the default path and sized accordingly
+  const bool b16 = h->use_tc && h->gemm_bf16 && h->use_tc_attn && N >= h->tc_min_rows;
+  const int elem = b16 ? 2 : 4;
   if (N > h->cap_tokens) {
-    float** bufs[] = {&h->h, &h->xn, &h->qkv, &h->att, &h->hid, &h->cond, &h->xbuf, &h->xbuf2};
+    float** bufs[] = {&h->h, &h->cond, &h->xbuf, &h->xbuf2};
     for (auto b : bufs) { dev_free(h, *b); *b = nullptr; }
-    // +128 rows of slack so tensor-core tiles may over-read the last partial tile
+    h->cap_tokens = 0;
     size_t n = (size_t)N + 128;
     TRY(dev_alloc_t(h, &h->h, n * kC));
-    TRY(dev_alloc_t(h, &h->xn, n * kC));
-    TRY(dev_alloc_t(h, &h->qkv, n * kQKV));
-    TRY(dev_alloc_t(h, &h->att, n * kC));
-    TRY(dev_alloc_t(h, &h->hid, n * kFF));
     TRY(dev_alloc_t(h, &h->cond, n * kC));
     TRY(dev_alloc_t(h, &h->xbuf, n * 28));
     TRY(dev_alloc_t(h, &h->xbuf2, n * 28));
     h->cap_tokens = N;
+  }
+  if ((N + 128) * elem > h->cap_op_bytes) {
+    float** bufs[] = {&h->xn, &h->qkv, &h->att, &h->hid};
+    for (auto b : bufs) { dev_free(h, *b); *b = nullptr; }
+    h->cap_op_bytes = 0;
+    // +128 rows of slack so tensor-core tiles may over-read the last partial tile
+    const size_t nb = (size_t)(N + 128) * elem;
+    TRY(dev_alloc(h, reinterpret_cast<void**>(&h->xn), nb * kC));
+    TRY(dev_alloc(h, reinterpret_cast<void**>(&h->qkv), nb * kQKV));
+    TRY(dev_alloc(h, reinterpret_cast<void**>(&h->att), nb * kC));
+    TRY(dev_alloc(h, reinterpret_cast<void**>(&h->hid), nb * kFF));
+    h->cap_op_bytes = (long long)nb;
   }
   if (rows > h->cap_rows) {
     float** bufs[] = {&h->xi, &h->xni, &h->proj, &h->cat, &h->qkvi, &h->atti, &h->hidi,
@@ -482,7 +497,7 @@ int run_ipa_trunk(mdgen_handle* h, cudaStream_t s, const mdgen_cond* c, int nrep
   ipa_init_kernel<<<(unsigned)rows, kC, 0, s>>>(two ? 1 : 0, c->start_rot, c->start_trans, c->end_rot,
                                                c->end_trans, c->aatype, h->cfg.use_aa_emb ? h->aa_emb : nullptr,
                                                h->wf, h->bf, h->wr, h->br, c->mask, T, L, h->xi, h->frot,
-                                               h->ftrans, h->fmask, BL);
+                                               h->ftrans, h->fmask, BL, two ? c->quat_sign : nullptr);
   CHECK_LAUNCH(h);
   SeqMap smi{L, rows / L, 1, (long long)L, 0, 1};
   for (int i = 0; i < n; ++i) {
@@ -662,9 +677,27 @@ int mdgen_set_tensor(mdgen_handle* h, const char* name, const float* data, int64
   return MDGEN_OK;
 }
 
+static int finalize_weights_impl(mdgen_handle* h, cudaStream_t s);
+
 int mdgen_finalize_weights(mdgen_handle* h, void* stream) {
   if (!h) return MDGEN_E_INVALID;
   cudaStream_t s = (cudaStream_t)stream;
+  // a reload replaces the previous generation of packed weights: wait for work that may still read them,
+  // then release them (every packed copy is re-created below)
+  if (!h->weight_allocs.empty()) {
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    std::vector<void*> old;
+    old.swap(h->weight_allocs);
+    for (void* p : old) dev_free(h, p);
+  }
+  h->finalized = false;
+  h->alloc_is_weight = true;
+  int rc = finalize_weights_impl(h, s);
+  h->alloc_is_weight = false;
+  return rc;
+}
+
+static int finalize_weights_impl(mdgen_handle* h, cudaStream_t s) {
   const mdgen_config& c = h->cfg;
   const int n = c.num_layers, D = c.latent_dim;
   const bool two_any = c.tps_condition || c.inpainting;
@@ -817,7 +850,7 @@ int mdgen_featurize_atom14(mdgen_handle* h, int32_t B, int32_t L, const float* a
 
 int mdgen_forward(mdgen_handle* h, const float* x, const float* t, const mdgen_cond* cond, float* out,
                   void* stream) {
-  if (!h || !x || !t || !out) { if (h) h->err = "mdgen_forward: null argument"; return MDGEN_E_INVALID; }
+  if (!h || !x || !t || !out || !cond) { if (h) h->err = "mdgen_forward: null argument"; return MDGEN_E_INVALID; }
   cudaStream_t s = (cudaStream_t)stream;
   h->trunk_precomputed = false;
   TRY(prepare_call(h, s, cond, cond ? cond->B : 0));
@@ -829,7 +862,7 @@ int mdgen_forward(mdgen_handle* h, const float* x, const float* t, const mdgen_c
 
 int mdgen_sample_euler(mdgen_handle* h, const float* zs, const float* t_grid, int32_t K,
                        const mdgen_cond* cond, float* x_out, void* stream) {
-  if (!h || !zs || !t_grid || !x_out || K < 1) { if (h) h->err = "mdgen_sample_euler: bad argument"; return MDGEN_E_INVALID; }
+  if (!h || !zs || !t_grid || !x_out || !cond || K < 1) { if (h) h->err = "mdgen_sample_euler: bad argument"; return MDGEN_E_INVALID; }
   cudaStream_t s = (cudaStream_t)stream;
   // the IPA trunk of all K steps is evaluated at once when its stacked rows stay modest
   const bool two_t = !h->cfg.sim_condition && (h->cfg.tps_condition || h->cfg.inpainting);

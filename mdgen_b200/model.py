@@ -10,7 +10,7 @@ import torch.nn as nn
 
 from ._lib import Engine, MDGenError
 from .config import (MDGenConfig, config_from_args, is_buffer, model_schema)
-from .rigid import as_rot_trans
+from .rigid import as_rot_trans, eigh_quat_sign
 from .synthetic import sincos_pos_embed
 
 
@@ -48,6 +48,12 @@ class LatentMDGenModel(nn.Module):
             _assign(self, name, t, is_buffer(name))
         self._engine = None
         self._engine_key = None
+        # Two-trunk (tps / inpainting) models only: sign convention of the relative start<->end quaternions.
+        #   "canonical": w >= 0 (deterministic; default)
+        #   "eigh" / "eigh_cpu": whatever torch.linalg.eigh returns on the frames' device / on the CPU, i.e. what
+        #   the reference feeds latent_to_emb_f/r (latent_model.py:194-195) on that backend - use the one the
+        #   checkpoint was trained with ("Eigenvector sign").
+        self.quat_sign_mode = "canonical"
 
     # -- engine management ---------------------------------------------------------------------
     def _weights_key(self):
@@ -68,15 +74,25 @@ class LatentMDGenModel(nn.Module):
                 self._engine_key = key
         return self._engine
 
+    def _quat_sign(self, start, end):
+        if torch.is_tensor(self.quat_sign_mode):          # explicit signs [2,B,L] (tests: the golden's own signs)
+            return self.quat_sign_mode.to(start[0].device) if self.cfg.two_trunks else None
+        if not self.cfg.two_trunks or self.quat_sign_mode == "canonical" or end is None:
+            return None
+        if self.quat_sign_mode not in ("eigh", "eigh_cpu"):
+            raise ValueError(f"quat_sign_mode {self.quat_sign_mode!r}")
+        return eigh_quat_sign(start, end, device="cpu" if self.quat_sign_mode == "eigh_cpu" else None)
+
     # -- reference surface ---------------------------------------------------------------------
     @torch.no_grad()
     def forward_inference(self, x, t, mask, start_frames=None, end_frames=None, x_cond=None,
                           x_cond_mask=None, aatype=None):
         """== mdgen/model/latent_model.py:263-269 (non-design)."""
         eng = self.engine()
+        start, end = as_rot_trans(start_frames), as_rot_trans(end_frames)
         with torch.cuda.device(x.device):
-            return eng.forward(x, t, mask, as_rot_trans(start_frames), as_rot_trans(end_frames),
-                               x_cond, x_cond_mask, aatype)
+            return eng.forward(x, t, mask, start, end, x_cond, x_cond_mask, aatype,
+                               quat_sign=self._quat_sign(start, end))
 
     def forward(self, *a, **k):
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
@@ -90,6 +106,7 @@ class LatentMDGenModel(nn.Module):
                      x_cond_mask=None, aatype=None):
         """All Euler steps inside the native library (no Python per step)."""
         eng = self.engine()
+        start, end = as_rot_trans(start_frames), as_rot_trans(end_frames)
         with torch.cuda.device(zs.device):
-            return eng.sample_euler(zs, t_grid, mask, as_rot_trans(start_frames),
-                                    as_rot_trans(end_frames), x_cond, x_cond_mask, aatype)
+            return eng.sample_euler(zs, t_grid, mask, start, end, x_cond, x_cond_mask, aatype,
+                                    quat_sign=self._quat_sign(start, end))

@@ -33,8 +33,14 @@ def sincos_pos_embed(embed_dim: int, n: int) -> np.ndarray:
     return np.concatenate([np.sin(out), np.cos(out)], axis=1).astype(np.float32)
 
 
-def synthetic_state_dict(cfg: MDGenConfig, seed: int = 0) -> "OrderedDict[str, torch.Tensor]":
-    """Full `LatentMDGenModel` state dict (keys without the wrapper's `model.` prefix)."""
+def synthetic_state_dict(cfg: MDGenConfig, seed: int = 0, stress: bool = False
+                         ) -> "OrderedDict[str, torch.Tensor]":
+    """Full `LatentMDGenModel` state dict (keys without the wrapper's `model.` prefix).
+
+    stress=True makes the weights "trained-like" in the ways that matter numerically: the query
+    projections of every token attention are scaled x6 (logit std ~6: sharp, near one-hot softmax rows),
+    the adaLN gates are ~1 instead of ~0.02 (every branch contributes at O(1) to the residual stream)
+    and the final projection is xavier-scaled (O(1) velocities)."""
     sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
     for name, shape in model_schema(cfg).items():
         g = _rng(seed, name)
@@ -59,6 +65,17 @@ def synthetic_state_dict(cfg: MDGenConfig, seed: int = 0) -> "OrderedDict[str, t
         else:  # Linear weights [out, in]: xavier-normal scale
             fan_out, fan_in = shape
             arr = math.sqrt(2.0 / (fan_in + fan_out)) * g.standard_normal(shape, dtype=np.float32)
+        if stress:
+            if name.startswith("layers.") and name.endswith(("attn.q_proj.weight", "attn.q_proj.bias")):
+                arr = 6.0 * arr
+            elif name.endswith("adaLN_modulation.1.bias"):
+                arr = arr.copy()
+                nchunk = arr.shape[0] // EMBED_DIM          # 6 (IPA layers) / 9 (main layers) / 2 (final)
+                for c in range(2, nchunk, 3):               # gate chunks: every third, starting at index 2
+                    arr[c * EMBED_DIM:(c + 1) * EMBED_DIM] += 1.0
+            elif name == "emb_to_latent.linear.weight":
+                fan_out, fan_in = shape
+                arr = math.sqrt(2.0 / (fan_in + fan_out)) * g.standard_normal(shape, dtype=np.float32)
         sd[name] = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float32))
     return sd
 

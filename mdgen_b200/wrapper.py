@@ -16,6 +16,9 @@ from .model import LatentMDGenModel
 from .rigid import Rigid, Rotation
 from .transport import Sampler, create_transport
 
+DESIGN_IDX = [1, 2]      # mdgen/wrapper.py:30-32
+COND_IDX = [0, 3]
+
 try:  # the reference subclasses pl.LightningModule (mdgen/wrapper.py:46)
     import pytorch_lightning as pl
     _Base = pl.LightningModule
@@ -65,12 +68,20 @@ class NewMDGenWrapper(_Base):
         eng = self.model.engine()
         rots, trans = batch["rots"], batch["trans"]
         B, T, L = trans.shape[:3]
+        torsions = batch["torsions"]
+        if self.args.no_design_torsion and not self.args.no_torsion:       # wrapper.py:322-325
+            torsions = torsions.clone()
+            torsions[:, :, DESIGN_IDX] = 0
         with torch.cuda.device(trans.device):
-            latents, x_cond, cond_mask = eng.prep_batch(rots, trans, batch["torsions"])
+            latents, x_cond, cond_mask = eng.prep_batch(rots, trans, torsions)
         rigids = Rigid(Rotation(rots), trans)
         D = self.latent_dim
         frame_loss_mask = batch["mask"].unsqueeze(-1).expand(-1, -1, D - 14)
         torsion_loss_mask = batch["torsion_mask"].unsqueeze(-1).expand(-1, -1, -1, 2).reshape(B, L, 14)
+        if self.args.supervise_all_torsions:                                # wrapper.py:329-332
+            torsion_loss_mask = torch.ones_like(torsion_loss_mask)
+        elif self.args.supervise_no_torsions:
+            torsion_loss_mask = torch.zeros_like(torsion_loss_mask)
         loss_mask = torch.cat([frame_loss_mask, torsion_loss_mask], -1).unsqueeze(1).expand(-1, T, -1, -1)
         return {
             "rigids": rigids,

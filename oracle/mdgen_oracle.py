@@ -252,11 +252,16 @@ def mdgen_layer(sd, prefix, x, temb, mask):
     return res + g_m * h                                                              # :481
 
 
+# The reference leaves torch.linalg.eigh's arbitrary eigenvector sign on the relative quaternions of the
+# two-trunk branch (mdgen/model/latent_model.py:194-195). True: canonicalise w >= 0 (deterministic across
+# LAPACK / cuSOLVER builds; the product's default "canonical" mode). False: keep eigh's sign, i.e. the
+# unmodified reference on this backend (the product's quat_sign_mode "eigh" / "eigh_cpu").
+CANONICAL_TPS_QUAT = True
+
+
 def run_ipa(sd, cfg, temb, mask_bl, start, end, aatype):
     """LatentMDGenModel.run_ipa — mdgen/model/latent_model.py:175-210.
-    start/end = (R [B,L,3,3], t [B,L,3]). Deviation (documented in DESIGN.md): the tps branch
-    canonicalises the relative quaternion to w >= 0, the reference leaves eigh's arbitrary sign
-    (mdgen/model/latent_model.py:194-195)."""
+    start/end = (R [B,L,3,3], t [B,L,3]). See CANONICAL_TPS_QUAT for the sign of the tps-branch quaternions."""
     B, L = mask_bl.shape
     n = cfg.num_layers
     if cfg.sim_condition:
@@ -268,8 +273,8 @@ def run_ipa(sd, cfg, temb, mask_bl, start, end, aatype):
         return x
     Rs, ts = start
     Re, te = end
-    x_f = to_tensor_7(*rigid_compose(*rigid_invert(Rs, ts), Re, te))                  # :194
-    x_r = to_tensor_7(*rigid_compose(*rigid_invert(Re, te), Rs, ts))                  # :195
+    x_f = to_tensor_7(*rigid_compose(*rigid_invert(Rs, ts), Re, te), canonical=CANONICAL_TPS_QUAT)   # :194
+    x_r = to_tensor_7(*rigid_compose(*rigid_invert(Re, te), Rs, ts), canonical=CANONICAL_TPS_QUAT)   # :195
     x_f = F.linear(x_f, sd["latent_to_emb_f.weight"], sd["latent_to_emb_f.bias"])
     x_r = F.linear(x_r, sd["latent_to_emb_r.weight"], sd["latent_to_emb_r.bias"])
     if aatype is not None and cfg.use_aa_emb:

@@ -1,8 +1,9 @@
-"""Import the UNMODIFIED reference (/root/reference) in the build container.
+"""Import the UNMODIFIED reference: from /root/reference in the build container, else from the
+byte-identical git-ignored copy `oracle/_ref` made by `oracle/vendor_reference.py` (the copy travels
+to the GPU box with the snapshot; its MANIFEST.json pins every file's sha256).
 
-TEST INFRASTRUCTURE. /root/reference does not exist on the GPU box, so nothing that runs
-there may call into this file; it is used by tests/golden/gen_golden.py (here) and by the
-`-m "not gpu"` tests that cross-check the oracle against the live reference when present.
+TEST / BENCH INFRASTRUCTURE. Used by tests/golden/gen_golden.py (here), by the tests that
+cross-check against the live reference, and by bench.py's reference legs. Never by the product.
 
 Recipe: put the stand-in third-party modules (oracle/ref_shims) and
 /root/reference on sys.path, set MODEL_DIR to a scratch dir (mdgen/logger.py opens
@@ -17,12 +18,34 @@ import os
 import sys
 import tempfile
 
-REFERENCE_ROOT = os.environ.get("MDGEN_REFERENCE_ROOT", "/root/reference")
-_SHIMS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_shims")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SHIMS = os.path.join(_HERE, "ref_shims")
+
+
+def _resolve_root():
+    for root in (os.environ.get("MDGEN_REFERENCE_ROOT", "/root/reference"), os.path.join(_HERE, "_ref")):
+        if os.path.isfile(os.path.join(root, "mdgen", "wrapper.py")):
+            return root
+    return None
+
+
+REFERENCE_ROOT = _resolve_root()
 
 
 def reference_available() -> bool:
-    return os.path.isfile(os.path.join(REFERENCE_ROOT, "mdgen", "wrapper.py"))
+    return REFERENCE_ROOT is not None
+
+
+def reference_kind() -> str:
+    """'live' (/root/reference), 'vendored' (oracle/_ref, sha256-verified) or 'absent'."""
+    if REFERENCE_ROOT is None:
+        return "absent"
+    if os.path.abspath(REFERENCE_ROOT) == os.path.join(_HERE, "_ref"):
+        from . import vendor_reference
+        if not vendor_reference.verify():
+            raise RuntimeError("oracle/_ref does not match its MANIFEST.json (not the unmodified reference)")
+        return "vendored"
+    return "live"
 
 
 _loaded = None
@@ -34,7 +57,8 @@ def load_reference():
     if _loaded is not None:
         return _loaded
     if not reference_available():
-        raise RuntimeError(f"reference not found under {REFERENCE_ROOT}")
+        raise RuntimeError("reference not found (neither /root/reference nor oracle/_ref)")
+    reference_kind()
     os.environ.setdefault("MODEL_DIR", tempfile.mkdtemp(prefix="mdgen_ref_"))
     os.environ.setdefault("WANDB_MODE", "disabled")
     for p in (REFERENCE_ROOT, _SHIMS):
@@ -84,3 +108,45 @@ def make_args(**overrides) -> argparse.Namespace:
     )
     d.update(overrides)
     return argparse.Namespace(**d)
+
+
+def chunked_eigh_patch(chunk=8192):
+    """Context manager: torch.linalg.eigh evaluated in batches of `chunk` matrices. cuSOLVER's batched
+    syevj refuses the 256,000 4x4 matrices of `rot_to_quat` (mdgen/rigid_utils.py:191-210) at BASELINE
+    configs[1]; splitting the batch changes no value. A patch on torch, not on the reference."""
+    import contextlib
+
+    import torch
+
+    @contextlib.contextmanager
+    def cm():
+        orig = torch.linalg.eigh
+
+        def eigh(a, *args, **kw):
+            if a.dim() < 3 or a.shape[:-2].numel() <= chunk:
+                return orig(a, *args, **kw)
+            flat = a.reshape(-1, a.shape[-2], a.shape[-1])
+            ws, vs = [], []
+            for i in range(0, flat.shape[0], chunk):
+                w, v = orig(flat[i:i + chunk], *args, **kw)
+                ws.append(w); vs.append(v)
+            return (torch.cat(ws).reshape(*a.shape[:-2], a.shape[-1]),
+                    torch.cat(vs).reshape(a.shape))
+
+        torch.linalg.eigh = eigh
+        try:
+            yield
+        finally:
+            torch.linalg.eigh = orig
+
+    return cm()
+
+
+def reference_wrapper(args, sd, device="cpu"):
+    """The reference's own NewMDGenWrapper with `sd` loaded strictly into its model, in eval mode."""
+    import torch
+    wrapper_mod = load_reference()
+    torch.manual_seed(0)
+    m = wrapper_mod.NewMDGenWrapper(args).eval()
+    m.model.load_state_dict(sd, strict=True)
+    return m.to(device)

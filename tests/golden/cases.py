@@ -21,4 +21,10 @@ CASES = {
     "inpaint": dict(args=dict(inpainting=True, prepend_ipa=True, abs_pos_emb=True, crop=4,
                               num_frames=10, no_aa_emb=True, no_torsion=True),
                     B=2, T=10, L=4, K=3, t_fwd=[0.4, 0.8], canonical_quat=True),
+    # "trained-like" stress weights (synthetic_state_dict(stress=True): sharp softmax rows, O(1) gates and
+    # velocities) on a time axis long enough for the tcgen05 attention (3 key tiles, ragged tail)
+    "stress": dict(args=dict(_SIM, num_frames=200), B=1, T=200, L=4, K=3, t_fwd=[0.45], stress=True),
+    # the same weights on an ATLAS-shaped chain (residue attention over 80 residues with padding)
+    "stress_atlas": dict(args=dict(sim_condition=True, prepend_ipa=True, crop=80, num_frames=10),
+                         B=1, T=10, L=80, K=2, t_fwd=[0.7], batch=dict(pad_last=7), stress=True),
 }

@@ -17,7 +17,7 @@ def load_case(name):
     case = CASES[name]
     args = default_args(**case["args"])
     cfg = config_from_args(args)
-    sd = synthetic_state_dict(cfg, seed=0)
+    sd = synthetic_state_dict(cfg, seed=0, stress=bool(case.get("stress")))
     batch = synthetic_batch(case["B"], case["T"], case["L"], seed=1, **case.get("batch", {}))
     zs = synthetic_noise(case["B"], case["T"], case["L"], cfg.latent_dim, seed=2)
     g = dict(np.load(os.path.join(GOLDEN, f"{name}.npz")))

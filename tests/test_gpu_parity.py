@@ -79,6 +79,29 @@ def test_golden_cases(name, path):
     assert (aa.cpu().numpy() == g["aa_out"]).all()
 
 
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("name", [n for n, c in CASES.items() if c.get("canonical_quat")])
+def test_two_trunk_follows_reference_eigh_sign(name, path):
+    """tps / inpainting against the UNPATCHED reference: with the eigenvector signs the reference's own
+    torch.linalg.eigh produced (golden `quat_sign`), the CUDA path reproduces its velocities and Euler state;
+    `quat_sign_mode="eigh_cpu"` derives the same signs by making the same LAPACK call."""
+    case, args, cfg, sd, batch, zs, g = load_case(name)
+    args.sampling_method = "euler"
+    m = _wrapper(args, sd, path)
+    tol = TOL_SIMT if path == "simt" else TOL
+    kw = m.prep_batch(_dev(batch))["model_kwargs"]
+    t = torch.tensor(case["t_fwd"]).cuda()
+    for mode in (torch.from_numpy(g["quat_sign"]), "eigh_cpu"):
+        m.model.quat_sign_mode = mode
+        v = m.model.forward_inference(zs.cuda(), t, **kw)
+        assert max_rel(v.cpu(), g["v_eigh"]) < tol, (mode, max_rel(v.cpu(), g["v_eigh"]))
+        xk = m.model.sample_euler(zs.cuda(), euler_time_grid(case["K"]), **kw)
+        assert max_rel(xk.cpu(), g["x_euler_eigh"]) < tol, (mode, max_rel(xk.cpu(), g["x_euler_eigh"]))
+    m.model.quat_sign_mode = "canonical"
+    v = m.model.forward_inference(zs.cuda(), t, **kw)
+    assert max_rel(v.cpu(), g["v"]) < tol
+
+
 _ORACLE_CACHE = {}
 
 

@@ -79,7 +79,7 @@ def test_library_loads_and_exports_header_symbols():
     for sym in declared:
         assert hasattr(lib, sym), f"{sym} declared in include/mdgen_b200.h but not exported"
     assert set(_lib.EXPORTS) == declared
-    assert lib.mdgen_abi_version() == 1
+    assert lib.mdgen_abi_version() == 2
 
 
 def test_create_fails_loudly_without_gpu():

@@ -37,6 +37,33 @@ def test_oracle_matches_reference_golden(name):
     assert (g["aa_out"] == batch["seqres"][:, None].expand(-1, case["T"], -1).numpy()).all()
 
 
+@pytest.mark.parametrize("name", [n for n, c in CASES.items() if c.get("canonical_quat")])
+def test_oracle_follows_unpatched_reference_eigh_sign(name):
+    """Two-trunk configs: the UNPATCHED reference keeps torch.linalg.eigh's eigenvector sign on the relative
+    quaternions (latent_model.py:194-195). With CANONICAL_TPS_QUAT off the oracle makes the same LAPACK call
+    and must reproduce the unpatched goldens; the product's sign helper must return the signs the reference
+    used. (The canonical goldens of the same case differ from these by up to 86 % of max|v|: the sign matters.)"""
+    from mdgen_b200.rigid import eigh_quat_sign
+    torch.set_num_threads(8)
+    case, args, cfg, sd, batch, zs, g = load_case(name)
+    prep = O.prep_batch(cfg, batch)
+    sign = eigh_quat_sign(prep["start"], prep["end"], device="cpu")
+    assert (sign.numpy() == g["quat_sign"]).all(), "torch.linalg.eigh sign differs from golden generation"
+    assert (g["quat_sign"] < 0).any() and (g["quat_sign"] > 0).any()
+    kw = dict(mask=prep["mask"], start=prep["start"], end=prep["end"], x_cond=prep["x_cond"],
+              x_cond_mask=prep["x_cond_mask"], aatype=prep["aatype"])
+    O.CANONICAL_TPS_QUAT = False
+    try:
+        with torch.no_grad():
+            v = O.forward(sd, cfg, zs, torch.tensor(case["t_fwd"]), **kw)
+            xk = O.sample_euler(sd, cfg, zs, euler_time_grid(case["K"]), **kw)
+    finally:
+        O.CANONICAL_TPS_QUAT = True
+    assert max_rel(v, g["v_eigh"]) < TOL_FWD, max_rel(v, g["v_eigh"])
+    assert max_rel(xk, g["x_euler_eigh"]) < TOL_EULER
+    assert max_rel(torch.from_numpy(g["v_eigh"]), g["v"]) > 1e-2      # the two conventions really differ
+
+
 def test_rope_shim_matches_hf_esm_port():
     """The fair-esm rotary embedding restated in oracle/ref_shims is bit-identical to the
     independent HF transformers port (the only offline cross-check for this un-vendored dep)."""

@@ -76,6 +76,119 @@ int run_throughput(int num_sms, int warps, int ctas_per_sm, unsigned long long* 
   return 0;
 }
 
+
+// ---------------------------------------------------------------- part 3
+// MUFU ex2 throughput per SM: fp32 (one result per lane-op), f16x2 and bf16x2 (two results per lane-op).
+// 8 independent dependency chains per thread, 16 warps per CTA, 2 CTAs per SM.
+template <int KIND>
+__global__ void __launch_bounds__(512) ex2_throughput_kernel(int reps, unsigned long long* cycles, uint32_t* sink) {
+  uint32_t x[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) x[i] = (KIND == 0) ? __float_as_uint(-0.001f * (threadIdx.x + i)) : (KIND == 1 ? 0xB000B400u : 0xBE00BE80u) + i;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int r = 0; r < reps; ++r) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (KIND == 0) { float y; asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(__uint_as_float(x[i]))); x[i] = __float_as_uint(y) ^ 0x80000000u; }
+      if (KIND == 1) { uint32_t y; asm volatile("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x[i])); x[i] = y ^ 0x80008000u; }
+      if (KIND == 2) { uint32_t y; asm volatile("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(y) : "r"(x[i])); x[i] = y ^ 0x80008000u; }
+    }
+  }
+  const long long t1 = clock64();
+  uint32_t acc = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc ^= x[i];
+  if (acc == 0x12345678u) sink[0] = acc;
+  if (threadIdx.x == 0) cycles[blockIdx.x] = (unsigned long long)(t1 - t0);
+}
+
+template <int KIND>
+int run_ex2(int num_sms, unsigned long long* d_cycles, uint32_t* d_sink) {
+  const int reps = 2048, grid = num_sms * 2;
+  ex2_throughput_kernel<KIND><<<grid, 512>>>(reps, d_cycles, d_sink);
+  CK(cudaDeviceSynchronize());
+  std::vector<unsigned long long> cyc(grid);
+  CK(cudaMemcpy(cyc.data(), d_cycles, grid * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  double mean = 0;
+  for (auto c : cyc) mean += (double)c;
+  mean /= grid;
+  const double instr_per_sm = 2.0 * 512 * reps * 8;
+  const char* nm = KIND == 0 ? "ex2.approx.ftz.f32   " : (KIND == 1 ? "ex2.approx.f16x2     " : "ex2.approx.ftz.bf16x2");
+  printf("  %s: %6.2f lane-instr/clk/SM = %6.2f exponentials/clk/SM  (%.0f cycles; includes one XOR per ex2)\n", nm,
+         instr_per_sm / mean, instr_per_sm / mean * (KIND == 0 ? 1 : 2), mean);
+  return 0;
+}
+
+// ---------------------------------------------------------------- part 4
+// tcgen05.ld with two x16 / x32 loads in flight per warp (the attention kernel's double-buffered pattern) and
+// tcgen05.st throughput.
+template <int X, bool STORE>
+__global__ void __launch_bounds__(512) ld2_throughput_kernel(int reps, int cols, unsigned long long* cycles, uint32_t* sink) {
+  __shared__ uint32_t slot;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32(&slot)), "r"((uint32_t)cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t base = slot + ((uint32_t)((warp & 3) * 32) << 16);
+  uint32_t acc = 0;
+  const long long t0 = clock64();
+  if (!STORE) {
+    uint32_t a[X], b[X];
+    if (X == 16) tc_ld16(base, reinterpret_cast<uint32_t(&)[16]>(a)); else tc_ld32(base, reinterpret_cast<uint32_t(&)[32]>(a));
+    for (int r = 0; r < reps; r += 2) {
+      const uint32_t c1 = (uint32_t)(((r + 1) * X) % (cols - X + 1)) & ~7u, c2 = (uint32_t)(((r + 2) * X) % (cols - X + 1)) & ~7u;
+      tc_ld_wait();
+      if (X == 16) tc_ld16(base + c1, reinterpret_cast<uint32_t(&)[16]>(b)); else tc_ld32(base + c1, reinterpret_cast<uint32_t(&)[32]>(b));
+      acc ^= a[0] ^ a[X - 1];
+      tc_ld_wait();
+      if (X == 16) tc_ld16(base + c2, reinterpret_cast<uint32_t(&)[16]>(a)); else tc_ld32(base + c2, reinterpret_cast<uint32_t(&)[32]>(a));
+      acc ^= b[0] ^ b[X - 1];
+    }
+    tc_ld_wait();
+    acc ^= a[1];
+  } else {
+    uint32_t a[X];
+#pragma unroll
+    for (int i = 0; i < X; ++i) a[i] = threadIdx.x + i;
+    for (int r = 0; r < reps; ++r) {
+      const uint32_t c1 = (uint32_t)((r * X) % (cols - X + 1)) & ~7u;
+      if (X == 16) tc_st16(base + c1, reinterpret_cast<uint32_t(&)[16]>(a)); else tc_st32(base + c1, reinterpret_cast<uint32_t(&)[32]>(a));
+      a[0] += r;
+    }
+    tc_st_wait();
+  }
+  const long long t1 = clock64();
+  if (acc == 0x12345678u) sink[0] = acc;
+  if (threadIdx.x == 0) cycles[blockIdx.x] = (unsigned long long)(t1 - t0);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(slot), "r"((uint32_t)cols) : "memory");
+}
+
+template <int X, bool STORE>
+int run_ld2(int num_sms, int warps, int ctas_per_sm, unsigned long long* d_cycles, uint32_t* d_sink) {
+  const int reps = 4096, cols = ctas_per_sm == 1 ? 512 : 256;
+  const int grid = num_sms * ctas_per_sm;
+  ld2_throughput_kernel<X, STORE><<<grid, warps * 32, 0>>>(reps, cols, d_cycles, d_sink);
+  CK(cudaDeviceSynchronize());
+  std::vector<unsigned long long> cyc(grid);
+  CK(cudaMemcpy(cyc.data(), d_cycles, grid * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  double mean = 0;
+  for (auto c : cyc) mean += (double)c;
+  mean /= grid;
+  const double bytes_per_sm = (double)ctas_per_sm * warps * reps * X * 32 * 4;
+  printf("  %s 32x32b.x%-2d %s %2d warps/CTA  %d CTA/SM : %7.1f B/clk/SM  (%.0f cycles)\n", STORE ? "st" : "ld", X,
+         STORE ? "            " : "2 in flight,", warps, ctas_per_sm, bytes_per_sm / mean, mean);
+  return 0;
+}
+
 // ---------------------------------------------------------------- part 2
 // D[128 x 32] = A[128 x 16] * B[32 x 16]^T with fp16 operands; A[i][k] = (k == i % 16), B[n][k] = n + 100 k
 // => D[i][n] = n + 100 (i % 16), exactly representable in fp16. c_format selects F16 (0) or F32 (1) accumulators.
@@ -202,5 +315,17 @@ int main() {
     for (int c = 0; c < 64; ++c) touched += (o[c] != 0xDEAD0000u);
     printf("    columns written in row 0: %d of 64 (N = 32 outputs)\n", touched);
   }
+  printf("part 3: MUFU ex2 throughput\n");
+  if (run_ex2<0>(num_sms, d_cycles, d_sink)) return 1;
+  if (run_ex2<1>(num_sms, d_cycles, d_sink)) return 1;
+  if (run_ex2<2>(num_sms, d_cycles, d_sink)) return 1;
+  printf("part 4: tcgen05.ld with two loads in flight per warp / tcgen05.st\n");
+  for (int ctas = 1; ctas <= 2; ++ctas)
+    for (int warps : {4, 8, 16}) {
+      if (run_ld2<16, false>(num_sms, warps, ctas, d_cycles, d_sink)) return 1;
+      if (run_ld2<32, false>(num_sms, warps, ctas, d_cycles, d_sink)) return 1;
+      if (run_ld2<16, true>(num_sms, warps, ctas, d_cycles, d_sink)) return 1;
+      if (run_ld2<32, true>(num_sms, warps, ctas, d_cycles, d_sink)) return 1;
+    }
   return 0;
 }
