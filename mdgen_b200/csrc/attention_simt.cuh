@@ -31,21 +31,21 @@ __device__ __forceinline__ long long seq_token(const SeqMap& sm, long long s, in
 }
 
 struct AttnParams {
-  const void* qkv;      // [N, 1152] fp32, or bf16 when qkv_bf16 (written by the bf16 QKV GEMM epilogue)
-  int qkv_bf16;
+  const void* qkv;      // [N, 1152] fp32, bf16 or fp16 (written in that format by the QKV GEMM epilogue)
+  int qkv_fmt;          // kFmtF32 / kFmtBF16 / kFmtF16
   const float* mask;    // [N] 1 = real token (key padding = 1 - mask), may be nullptr
   const float* bias_k;  // [384] raw (rotated at position S inside the kernel)
   const float* bias_v;  // [384]
   const float* cosT;    // [>= S+1, 12]
   const float* sinT;
-  void* out;            // [N, 384] fp32, or bf16 when round_out == 3
+  void* out;            // [N, 384] fp32, bf16 (round_out == 3) or fp16 (round_out == 4)
   int round_out;        // operand rounding / storage mode of the output (see store_operand4)
   SeqMap sm;
 };
 
 // 24 consecutive projection values (one head of q, k or v) starting at element `idx` of qkv
-__device__ __forceinline__ void load24(const void* qkv, size_t idx, int bf16, float* out) {
-  if (bf16) {
+__device__ __forceinline__ void load24(const void* qkv, size_t idx, int fmt, float* out) {
+  if (fmt != kFmtF32) {
     const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(qkv) + idx);
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
@@ -53,8 +53,9 @@ __device__ __forceinline__ void load24(const void* qkv, size_t idx, int bf16, fl
       const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        out[8 * i + 2 * j] = __uint_as_float(w[j] << 16);
-        out[8 * i + 2 * j + 1] = __uint_as_float(w[j] & 0xFFFF0000u);
+        const float2 f = unpack_half2(w[j], fmt);
+        out[8 * i + 2 * j] = f.x;
+        out[8 * i + 2 * j + 1] = f.y;
       }
     }
   } else {
@@ -85,7 +86,7 @@ __global__ void __launch_bounds__(128) attn_small_kernel(AttnParams p) {
   long long s = r / sm.S;
   long long tq = seq_token(sm, s, e);
   float q[kHD], acc[kHD];
-  load24(p.qkv, (size_t)tq * kQKV + h * kHD, p.qkv_bf16, q);
+  load24(p.qkv, (size_t)tq * kQKV + h * kHD, p.qkv_fmt, q);
   rope24(q, p.cosT + e * kHalf, p.sinT + e * kHalf);
 #pragma unroll
   for (int i = 0; i < kHD; ++i) acc[i] = 0.f;
@@ -95,8 +96,8 @@ __global__ void __launch_bounds__(128) attn_small_kernel(AttnParams p) {
     if (j < sm.S) {
       long long tk = seq_token(sm, s, j);
       if (p.mask && p.mask[tk] == 0.f) continue;
-      load24(p.qkv, (size_t)tk * kQKV + kC + h * kHD, p.qkv_bf16, k);
-      load24(p.qkv, (size_t)tk * kQKV + 2 * kC + h * kHD, p.qkv_bf16, v);
+      load24(p.qkv, (size_t)tk * kQKV + kC + h * kHD, p.qkv_fmt, k);
+      load24(p.qkv, (size_t)tk * kQKV + 2 * kC + h * kHD, p.qkv_fmt, v);
     } else {
 #pragma unroll
       for (int i = 0; i < kHD; ++i) { k[i] = p.bias_k[h * kHD + i]; v[i] = p.bias_v[h * kHD + i]; }
@@ -134,9 +135,9 @@ __global__ void __launch_bounds__(256) attn_l4_kernel(AttnParams p) {
   const int tl = lane >> 3, h = (int)(w & 1) * 8 + (lane & 7);
   const long long tok = seq_token(sm, s, tl);
   float q[kHD], k[kHD], v[kHD];
-  load24(p.qkv, (size_t)tok * kQKV + h * kHD, p.qkv_bf16, q);
-  load24(p.qkv, (size_t)tok * kQKV + kC + h * kHD, p.qkv_bf16, k);
-  load24(p.qkv, (size_t)tok * kQKV + 2 * kC + h * kHD, p.qkv_bf16, v);
+  load24(p.qkv, (size_t)tok * kQKV + h * kHD, p.qkv_fmt, q);
+  load24(p.qkv, (size_t)tok * kQKV + kC + h * kHD, p.qkv_fmt, k);
+  load24(p.qkv, (size_t)tok * kQKV + 2 * kC + h * kHD, p.qkv_fmt, v);
   rope24(q, p.cosT + tl * kHalf, p.sinT + tl * kHalf);
   rope24(k, p.cosT + tl * kHalf, p.sinT + tl * kHalf);
   const float valid = (p.mask == nullptr || p.mask[tok] != 0.f) ? 1.f : 0.f;
@@ -197,14 +198,14 @@ __global__ void __launch_bounds__(128) attn_l4s_kernel(AttnParams p) {
   const int tl = lane >> 3, hh = lane & 7, h = (int)(w & 1) * 8 + hh;
   const long long tok = seq_token(sm, s, tl);
   float q[kHD], t[kHD];
-  load24(p.qkv, (size_t)tok * kQKV + h * kHD, p.qkv_bf16, q);
-  load24(p.qkv, (size_t)tok * kQKV + kC + h * kHD, p.qkv_bf16, t);
+  load24(p.qkv, (size_t)tok * kQKV + h * kHD, p.qkv_fmt, q);
+  load24(p.qkv, (size_t)tok * kQKV + kC + h * kHD, p.qkv_fmt, t);
   rope24(q, p.cosT + tl * kHalf, p.sinT + tl * kHalf);
   rope24(t, p.cosT + tl * kHalf, p.sinT + tl * kHalf);
 #pragma unroll
   for (int i = 0; i < 6; ++i)
     *reinterpret_cast<float4*>(&ks[wib][tl][hh][4 * i]) = make_float4(t[4*i], t[4*i+1], t[4*i+2], t[4*i+3]);
-  load24(p.qkv, (size_t)tok * kQKV + 2 * kC + h * kHD, p.qkv_bf16, t);
+  load24(p.qkv, (size_t)tok * kQKV + 2 * kC + h * kHD, p.qkv_fmt, t);
 #pragma unroll
   for (int i = 0; i < 6; ++i)
     *reinterpret_cast<float4*>(&vs[wib][tl][hh][4 * i]) = make_float4(t[4*i], t[4*i+1], t[4*i+2], t[4*i+3]);
@@ -279,7 +280,7 @@ __global__ void __launch_bounds__(128) attn_flash_simt_kernel(AttnParams p) {
     qok[u] = e < sm.S;
     int ee = qok[u] ? e : sm.S - 1;
     tq[u] = seq_token(sm, s, ee);
-    load24(p.qkv, (size_t)tq[u] * kQKV + h * kHD, p.qkv_bf16, q[u]);
+    load24(p.qkv, (size_t)tq[u] * kQKV + h * kHD, p.qkv_fmt, q[u]);
     rope24(q[u], p.cosT + ee * kHalf, p.sinT + ee * kHalf);
 #pragma unroll
     for (int i = 0; i < kHD; ++i) { q[u][i] *= LOG2E; acc[u][i] = 0.f; }   // scores in log2 units

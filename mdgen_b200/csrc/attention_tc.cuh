@@ -173,8 +173,8 @@ __global__ void __launch_bounds__(256) attn_prep_kernel(AttnParams p, uint8_t* _
     float mval = 0.f;
     if (j < S) {
       long long tk = seq_token(sm, s, j);
-      load24(p.qkv, (size_t)tk * kQKV + kC + h * kHD, p.qkv_bf16, k);
-      load24(p.qkv, (size_t)tk * kQKV + 2 * kC + h * kHD, p.qkv_bf16, v);
+      load24(p.qkv, (size_t)tk * kQKV + kC + h * kHD, p.qkv_fmt, k);
+      load24(p.qkv, (size_t)tk * kQKV + 2 * kC + h * kHD, p.qkv_fmt, v);
       if (p.mask && p.mask[tk] == 0.f) mval = -INFINITY;
     } else if (j == S) {
 #pragma unroll
@@ -268,10 +268,11 @@ __global__ void __launch_bounds__(256) attn_prep2_kernel(AttnParams p, uint8_t* 
         const uint32_t wk[4] = {uk.x, uk.y, uk.z, uk.w}, wv[4] = {uv.x, uv.y, uv.z, uv.w};
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          k[8 * i + 2 * c] = __uint_as_float(wk[c] << 16);
-          k[8 * i + 2 * c + 1] = __uint_as_float(wk[c] & 0xFFFF0000u);
-          v[8 * i + 2 * c] = __uint_as_float(wv[c] << 16);
-          v[8 * i + 2 * c + 1] = __uint_as_float(wv[c] & 0xFFFF0000u);
+          const float2 fk = unpack_half2(wk[c], p.qkv_fmt), fv = unpack_half2(wv[c], p.qkv_fmt);
+          k[8 * i + 2 * c] = fk.x;
+          k[8 * i + 2 * c + 1] = fk.y;
+          v[8 * i + 2 * c] = fv.x;
+          v[8 * i + 2 * c + 1] = fv.y;
         }
       }
       if (p.mask && p.mask[seq_token(sm, s, j)] == 0.f) mval = -INFINITY;
@@ -384,7 +385,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(AttnParams p, co
   if (tid < 128) {
     tq = seq_token(sm, s, e < S ? e : S - 1);
     float q[kHD];
-    load24(p.qkv, (size_t)tq * kQKV + h * kHD, p.qkv_bf16, q);
+    load24(p.qkv, (size_t)tq * kQKV + h * kHD, p.qkv_fmt, q);
     const int pe = e < S ? e : S - 1;
     rope24(q, p.cosT + pe * kHalf, p.sinT + pe * kHalf);
     float qn2 = 0.f;
@@ -705,7 +706,7 @@ __global__ void __launch_bounds__(atp_threads(NP), 2) attn_tcp_kernel(AttnParams
         const int pe = e < S ? e : S - 1;
         const long long tq = seq_token(sm, s, pe);
         float q[kHD];
-        load24(p.qkv, (size_t)tq * kQKV + h * kHD, p.qkv_bf16, q);
+        load24(p.qkv, (size_t)tq * kQKV + h * kHD, p.qkv_fmt, q);
         rope24(q, p.cosT + pe * kHalf, p.sinT + pe * kHalf);
         float qn2 = 0.f;
 #pragma unroll
@@ -971,7 +972,7 @@ inline int attn_tcp_launch(const AttnParams& p, uint8_t* scratch, int prep2, int
   const long long blocks = p.sm.num_seq * kH;
   const long long items = blocks * nqt;
   if (items > 0x7fffffffLL) { if (err) *err = "attn_tcp: too many work items"; return -2; }
-  if (prep2 && p.qkv_bf16)
+  if (prep2 && p.qkv_fmt)
     attn_prep2_kernel<true><<<(unsigned)(p.sm.num_seq * nkt * 2), 256, AP2_SMEM_BYTES, s>>>(p, scratch);
   else
     attn_prep_kernel<true><<<(unsigned)blocks, 256, 0, s>>>(p, scratch);
@@ -1016,7 +1017,7 @@ inline int attn_tc_launch_t(const AttnParams& p, uint8_t* scratch, int prep2, bo
   const int nqt = (p.sm.S + AT_QT - 1) / AT_QT;
   const int nkt = (p.sm.S + 1 + AT_KT - 1) / AT_KT;
   long long blocks = p.sm.num_seq * kH;
-  if (prep2 && p.qkv_bf16)
+  if (prep2 && p.qkv_fmt)
     attn_prep2_kernel<PV16><<<(unsigned)(p.sm.num_seq * nkt * 2), 256, AP2_SMEM_BYTES, s>>>(p, scratch);
   else
     attn_prep_kernel<PV16><<<(unsigned)blocks, 256, 0, s>>>(p, scratch);
@@ -1037,7 +1038,7 @@ inline int attn_tc_launch_t(const AttnParams& p, uint8_t* scratch, int prep2, bo
 //   timing experiments, results undefined: bit 4 (16) pre-pass only; bits 5-6 DBG mode of the persistent kernel
 // Default 3. Measured on B200 at B=64, T=1000, L=4 (profiles/r1_attention_ncu.md): 0 -> 2.20 ms per mha_t
 // launch, 1 -> 2.05, 3 -> 1.95, 7 -> 1.96-2.05, 15 -> 2.08.
-constexpr int kAttnVariantDefault = 3;
+constexpr int kAttnVariantDefault = 256;   // generation 8 (attention_v8.cuh); 3 = best generation-7 variant
 inline int attn_tc_launch(const AttnParams& p, uint8_t* scratch, int variant, cudaStream_t s, std::string* err) {
   const int p2 = (variant >> 1) & 1;
   const bool po = (variant & 16) != 0;

@@ -76,11 +76,34 @@ __device__ __forceinline__ uint32_t pack_bf16x2_rn(float lo, float hi) {
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
+__device__ __forceinline__ uint32_t pack_f16x2_rn(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+// packed pair of fp16 -> two floats (x = low half)
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t u) {
+  float2 r;
+  asm("{\n\t.reg .f16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}"
+      : "=f"(r.x), "=f"(r.y) : "r"(u));
+  return r;
+}
+// 16-bit storage formats of GEMM-operand activations / weights
+constexpr int kFmtF32 = 0, kFmtBF16 = 1, kFmtF16 = 2;
+__device__ __forceinline__ float2 unpack_half2(uint32_t u, int fmt) {
+  return fmt == kFmtF16 ? unpack_f16x2(u) : make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xFFFF0000u));
+}
 // Store 4 consecutive GEMM-operand values starting at element index `idx` of `base`:
 //   mode 0/1/2: fp32 storage (unrounded / TF32-rounded / bf16-rounded-in-fp32)
-//   mode 3    : true bf16 storage (the bf16 tensor-core GEMM path), 8 bytes
+//   mode 3    : true bf16 storage, 8 bytes       mode 4: true fp16 storage (the default tensor-core GEMM path:
+//               TF32's 11-bit significand at bf16's size and MMA rate)
 __device__ __forceinline__ void store_operand4(void* base, size_t idx, float4 v, int mode) {
-  if (mode == 3) {
+  if (mode == 4) {
+    uint2 pk;
+    pk.x = pack_f16x2_rn(v.x, v.y);
+    pk.y = pack_f16x2_rn(v.z, v.w);
+    *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(base) + idx) = pk;
+  } else if (mode == 3) {
     uint2 pk;
     pk.x = pack_bf16x2_rn(v.x, v.y);
     pk.y = pack_bf16x2_rn(v.z, v.w);

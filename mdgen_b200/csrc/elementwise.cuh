@@ -356,11 +356,16 @@ __global__ void pack_rows_kernel(const float* __restrict__ src, float* __restric
   dst[(size_t)(dst_row0 + r) * dst_ld + c] = v;
 }
 
-// fp32 -> bf16 (round-to-nearest-even) copy: bf16 weight copies for the kind::f16 GEMM path
+// fp32 -> bf16 / fp16 (round-to-nearest-even) copy: 16-bit weight copies for the kind::f16 GEMM path
 __global__ void to_bf16_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, long long n) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   dst[i] = (uint16_t)(pack_bf16x2_rn(src[i], 0.f) & 0xFFFFu);
+}
+__global__ void to_f16_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  dst[i] = (uint16_t)(pack_f16x2_rn(src[i], 0.f) & 0xFFFFu);
 }
 
 // RoPE tables for positions 0..n-1: cos/sin(pos * inv_freq[i]), i < 12

@@ -22,6 +22,7 @@ struct Epilogue {
   float* out;
   int ldo;
   int round_out;       // round result to TF32 (output only feeds another tensor-core GEMM)
+  int half_fmt;        // tensor-core kernel with 16-bit operands / output: kFmtBF16 or kFmtF16
 };
 
 template <int MODE>

@@ -128,6 +128,10 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// kind::f16 with fp16 operands: a_format = b_format = 0 (F16), fp32 accumulate
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                             uint32_t accumulate) {
   asm volatile(
@@ -186,11 +190,12 @@ __device__ __forceinline__ void tc_epilogue4(const Epilogue& ep, const float* ga
   *reinterpret_cast<float4*>(ep.out + (size_t)m * ep.ldo + n) = v;
 }
 
-// BF16IN : operands are bf16 (kind::f16 MMA, K-block = 64 elements = 128 bytes, UMMA_K = 16) instead of
+// BF16IN : operands are 16-bit - fp16 (default) or bf16, selected at run time by ep.half_fmt - (kind::f16 MMA,
+//          K-block = 64 elements = 128 bytes, UMMA_K = 16) instead of
 //          TF32-in-fp32 (kind::tf32, K-block = 32 elements, UMMA_K = 8). Same 128-byte swizzled rows,
 //          same descriptors and 32-byte K advance, twice the MMA rate and half the shared-memory/L2
 //          operand traffic per FLOP (which is what bounds the fp32-operand variant).
-// BF16OUT: the epilogue stores bf16 (the fc1 hidden activations, consumed only by the fc2 GEMM).
+// BF16OUT: the epilogue stores the same 16-bit format (q|k|v, the fc1 hidden activations).
 template <int MODE, bool BF16IN, bool BF16OUT>
 __global__ void __launch_bounds__(128 + 32 * tc_epi_warps(MODE), 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                          const __grid_constant__ CUtensorMap tmB, long long M,
@@ -255,7 +260,8 @@ __global__ void __launch_bounds__(128 + 32 * tc_epi_warps(MODE), 1) gemm_tc_kern
   } else if (warp == 1) {
     if (lane == 0) {
       // ===================== MMA issuer (one thread) =====================
-      constexpr uint32_t idesc = BF16IN ? umma_idesc_bf16(TC_BM, TC_BN) : umma_idesc_tf32(TC_BM, TC_BN);
+      const uint32_t idesc = BF16IN ? (ep.half_fmt == kFmtF16 ? umma_idesc_f16(TC_BM, TC_BN) : umma_idesc_bf16(TC_BM, TC_BN))
+                                    : umma_idesc_tf32(TC_BM, TC_BN);
       int stage = 0;
       uint32_t phase = 0;
       uint32_t it = 0;
@@ -364,8 +370,8 @@ __global__ void __launch_bounds__(128 + 32 * tc_epi_warps(MODE), 1) gemm_tc_kern
             if (ep.round_out) { a.x = round_operand(a.x, ep.round_out); a.y = round_operand(a.y, ep.round_out); a.z = round_operand(a.z, ep.round_out); a.w = round_operand(a.w, ep.round_out); }
             if (BF16OUT) {
               uint2 pk;
-              pk.x = pack_bf16x2(a.x, a.y);
-              pk.y = pack_bf16x2(a.z, a.w);
+              if (ep.half_fmt == kFmtF16) { pk.x = pack_f16x2_rn(a.x, a.y); pk.y = pack_f16x2_rn(a.z, a.w); }
+              else { pk.x = pack_bf16x2(a.x, a.y); pk.y = pack_bf16x2(a.z, a.w); }
               *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(ep.out) + (size_t)m * ep.ldo + n) = pk;
             } else {
               *reinterpret_cast<float4*>(ep.out + (size_t)m * ep.ldo + n) = a;

@@ -19,6 +19,7 @@
 #ifndef MDGEN_NO_TC
 #include "gemm_tc.cuh"
 #include "attention_tc.cuh"
+#include "attention_v8.cuh"
 #endif
 
 using namespace mdgen;
@@ -39,6 +40,7 @@ struct MhaW {
   float *wqkv_tc, *wo_tc;
   float *wqkv_bf, *wo_bf;   // bf16-rounded fp32 copies (precision experiments only)
   uint16_t *wqkv_b16, *wo_b16;   // true bf16 copies for the kind::f16 GEMM path
+  uint16_t *wqkv_f16, *wo_f16;   // fp16 copies (default operand format)
 };
 struct IpaLayerW {
   float *ln_g, *ln_b, *head_w, *wproj, *bproj, *wout, *bout, *wproj_tc, *wout_tc;
@@ -48,7 +50,7 @@ struct IpaLayerW {
 struct MainLayerW {
   MhaW mha_l, mha_t;
   float *w1, *b1, *w2, *b2, *w1_tc, *w2_tc, *w1_bf, *w2_bf;
-  uint16_t *w1_b16, *w2_b16;
+  uint16_t *w1_b16, *w2_b16, *w1_f16, *w2_f16;
 };
 
 struct ProfEntry {
@@ -72,7 +74,9 @@ struct mdgen_handle {
 #else
   int use_tc = 1;      // tcgen05 TF32 GEMMs for the token GEMMs (0 = fp32 SIMT validation path)
 #endif
-  int gemm_bf16 = 1;   // token GEMMs (QKV / out / fc1 / fc2) with bf16 operands (kind::f16); 0 = TF32 operands
+  // token GEMMs (QKV / out / fc1 / fc2): 2 = fp16 operands (kind::f16; TF32's 11-bit significand at half the
+  // bytes and twice the MMA rate - the default), 1 = bf16 operands, 0 = TF32 operands (kind::tf32)
+  int gemm_bf16 = 2;
   int emu_bf16 = 0;    // precision experiments: bit 0 MLP, bit 1 attention projections see bf16-rounded operands
   int use_graph = 1;                 // replay steps from a CUDA graph when the workload is launch-bound
   long long graph_max_tokens = 65536;
@@ -237,10 +241,16 @@ int tc_copy(mdgen_handle* h, cudaStream_t s, const float* src, size_t n, float**
   return MDGEN_OK;
 }
 
-// true bf16 copy of an fp32 matrix
+// true bf16 / fp16 copy of an fp32 matrix
 int b16_copy(mdgen_handle* h, cudaStream_t s, const float* src, size_t n, uint16_t** dst) {
   TRY(dev_alloc_t(h, dst, n));
   to_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src, *dst, (long long)n);
+  CHECK_LAUNCH(h);
+  return MDGEN_OK;
+}
+int f16_copy(mdgen_handle* h, cudaStream_t s, const float* src, size_t n, uint16_t** dst) {
+  TRY(dev_alloc_t(h, dst, n));
+  to_f16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src, *dst, (long long)n);
   CHECK_LAUNCH(h);
   return MDGEN_OK;
 }
@@ -255,6 +265,7 @@ int pack_mha(mdgen_handle* h, cudaStream_t s, const std::string& p, MhaW* w) {
   TRY(tc_copy(h, s, w->wqkv, (size_t)kQKV * kC, &w->wqkv_tc));
   TRY(tc_copy(h, s, w->wqkv, (size_t)kQKV * kC, &w->wqkv_bf, 2));
   TRY(b16_copy(h, s, w->wqkv, (size_t)kQKV * kC, &w->wqkv_b16));
+  TRY(f16_copy(h, s, w->wqkv, (size_t)kQKV * kC, &w->wqkv_f16));
   TRY(pack(h, s, p + "attn.q_proj.bias", 1, kC, w->bqkv, kQKV, 0, scale, 0));
   TRY(pack(h, s, p + "attn.k_proj.bias", 1, kC, w->bqkv + kC, kQKV, 0, 1.f, 0));
   TRY(pack(h, s, p + "attn.v_proj.bias", 1, kC, w->bqkv + 2 * kC, kQKV, 0, 1.f, 0));
@@ -262,6 +273,7 @@ int pack_mha(mdgen_handle* h, cudaStream_t s, const std::string& p, MhaW* w) {
   TRY(tc_copy(h, s, w->wo, (size_t)kC * kC, &w->wo_tc));
   TRY(tc_copy(h, s, w->wo, (size_t)kC * kC, &w->wo_bf, 2));
   TRY(b16_copy(h, s, w->wo, (size_t)kC * kC, &w->wo_b16));
+  TRY(f16_copy(h, s, w->wo, (size_t)kC * kC, &w->wo_f16));
   TRY(pack_new(h, s, p + "attn.out_proj.bias", 1, kC, &w->bo));
   TRY(pack_new(h, s, p + "attn.bias_k", 1, kC, &w->bias_k));
   TRY(pack_new(h, s, p + "attn.bias_v", 1, kC, &w->bias_v));
@@ -345,9 +357,12 @@ int ensure_workspace(mdgen_handle* h, long long N, long long rows, int modrows) 
 // W = fp32 master (SIMT paths), W_tc = tensor-core operand copy: TF32-rounded fp32, or true bf16 when
 // in_bf16 (then A is a bf16 buffer too); out_bf16: the epilogue stores bf16.
 int gemm(mdgen_handle* h, cudaStream_t s, int mode, const float* A, int lda, const float* W,
-         const void* W_tc, int ldw, long long M, int N, int K, const Epilogue& ep, const char* tag,
-         bool in_bf16 = false, bool out_bf16 = false) {
+         const void* W_tc, int ldw, long long M, int N, int K, const Epilogue& ep_in, const char* tag,
+         int half_fmt = 0 /*kFmtBF16 / kFmtF16: 16-bit A and W*/, bool out_bf16 = false /*16-bit output*/) {
   ProfScope ps(h, s, tag);
+  const bool in_bf16 = half_fmt != 0;
+  Epilogue ep = ep_in;
+  ep.half_fmt = half_fmt;
 #ifndef MDGEN_NO_TC
   if (h->use_tc && W_tc && M >= h->tc_min_rows && tc_gemm_supported(N, K, in_bf16)) {
     int rc = tc_gemm_launch(mode, A, lda, W_tc, ldw, M, N, K, ep, s, &h->err, in_bf16, out_bf16);
@@ -395,14 +410,14 @@ Epilogue make_epi_gate(const float* bias, float* x, int ldo, const ModRef& mod, 
 
 int attention(mdgen_handle* h, cudaStream_t s, const float* qkv, const float* mask, const MhaW& w,
               float* out, const SeqMap& sm, int round_out, const char* tag, bool allow_tc = true,
-              bool qkv_bf16 = false) {
+              int qkv_fmt = 0) {
   ProfScope ps(h, s, tag);
   AttnParams p;
-  p.qkv = qkv; p.qkv_bf16 = qkv_bf16 ? 1 : 0; p.mask = mask; p.bias_k = w.bias_k; p.bias_v = w.bias_v;
+  p.qkv = qkv; p.qkv_fmt = qkv_fmt; p.mask = mask; p.bias_k = w.bias_k; p.bias_v = w.bias_v;
   p.cosT = h->cosT; p.sinT = h->sinT; p.out = out; p.round_out = round_out; p.sm = sm;
 #ifndef MDGEN_NO_TC
   if (allow_tc && h->use_tc && h->use_tc_attn && sm.S > 64) {
-    size_t need = attn_tc_scratch_bytes(sm);
+    size_t need = std::max(attn_tc_scratch_bytes(sm), attn8_scratch_bytes(sm));
     if (need > h->attn_scratch_bytes) {
       if (h->attn_scratch) dev_free(h, h->attn_scratch);
       h->attn_scratch = nullptr; h->attn_scratch_bytes = 0;
@@ -410,7 +425,9 @@ int attention(mdgen_handle* h, cudaStream_t s, const float* qkv, const float* ma
       CUDA_TRY(h, cudaMemsetAsync(h->attn_scratch, 0, need, s));   // V^T pad rows must read as zeros
       h->attn_scratch_bytes = need;
     }
-    if (attn_tc_launch(p, h->attn_scratch, h->attn_variant, s, &h->err)) return MDGEN_E_CUDA;
+    if (h->attn_variant & 256) {     // generation 8 (default): fp16 operands, one softmax thread per query row
+      if (attn8_launch(p, h->attn_scratch, h->attn_variant & 255, s, &h->err)) return MDGEN_E_CUDA;
+    } else if (attn_tc_launch(p, h->attn_scratch, h->attn_variant, s, &h->err)) return MDGEN_E_CUDA;
     h->launches += 2;
     return MDGEN_OK;
   }
@@ -563,36 +580,42 @@ int run_step(mdgen_handle* h, cudaStream_t s, const mdgen_cond* c, const float* 
     // GEMM operand modes of the token GEMMs: 3 = true bf16 storage + kind::f16 MMA (default),
     // 1 = TF32-rounded fp32 + kind::tf32 MMA, 2 = bf16-rounded values through the TF32 MMA (precision
     // experiments, option "emu_bf16": bit 0 MLP, bit 1 attention projections), 0 = fp32 SIMT path.
-    const bool bf = rt && h->gemm_bf16 && tc_gemm_supported(kQKV, kC, true);
-    const bool bfq = bf && h->use_tc_attn;   // q|k|v stored as bf16 (the SIMT flash kernel reads fp32 only)
-    const int rm_attn = !rt ? 0 : (bf ? 3 : ((h->emu_bf16 & 2) ? 2 : 1));
-    const int rm_mlp = !rt ? 0 : (bf ? 3 : ((h->emu_bf16 & 1) ? 2 : 1));
-    const void* wqkv_l = bf ? (const void*)w.mha_l.wqkv_b16 : ((h->emu_bf16 & 2) ? w.mha_l.wqkv_bf : w.mha_l.wqkv_tc);
-    const void* wo_l = bf ? (const void*)w.mha_l.wo_b16 : ((h->emu_bf16 & 2) ? w.mha_l.wo_bf : w.mha_l.wo_tc);
-    const void* wqkv_t = bf ? (const void*)w.mha_t.wqkv_b16 : ((h->emu_bf16 & 2) ? w.mha_t.wqkv_bf : w.mha_t.wqkv_tc);
-    const void* wo_t = bf ? (const void*)w.mha_t.wo_b16 : ((h->emu_bf16 & 2) ? w.mha_t.wo_bf : w.mha_t.wo_tc);
-    const void* w1x = bf ? (const void*)w.w1_b16 : ((h->emu_bf16 & 1) ? w.w1_bf : w.w1_tc);
-    const void* w2x = bf ? (const void*)w.w2_b16 : ((h->emu_bf16 & 1) ? w.w2_bf : w.w2_tc);
+    const int hf = (rt && h->gemm_bf16 && tc_gemm_supported(kQKV, kC, true)) ? (h->gemm_bf16 == 2 ? kFmtF16 : kFmtBF16) : 0;
+    const bool bf = hf != 0;
+    const int hfq = (bf && h->use_tc_attn) ? hf : 0;   // q|k|v stored 16-bit (the SIMT flash kernel reads fp32 only)
+    const bool bfq = hfq != 0;
+    const int rm16 = hf == kFmtF16 ? 4 : 3;            // store_operand4 mode of the 16-bit format
+    const int rm_attn = !rt ? 0 : (bf ? rm16 : ((h->emu_bf16 & 2) ? 2 : 1));
+    const int rm_mlp = !rt ? 0 : (bf ? rm16 : ((h->emu_bf16 & 1) ? 2 : 1));
+    auto pick = [&](const uint16_t* f16, const uint16_t* b16, const float* emu, const float* tc, int emu_bit) -> const void* {
+      return bf ? (const void*)(hf == kFmtF16 ? f16 : b16) : ((h->emu_bf16 & emu_bit) ? (const void*)emu : (const void*)tc);
+    };
+    const void* wqkv_l = pick(w.mha_l.wqkv_f16, w.mha_l.wqkv_b16, w.mha_l.wqkv_bf, w.mha_l.wqkv_tc, 2);
+    const void* wo_l = pick(w.mha_l.wo_f16, w.mha_l.wo_b16, w.mha_l.wo_bf, w.mha_l.wo_tc, 2);
+    const void* wqkv_t = pick(w.mha_t.wqkv_f16, w.mha_t.wqkv_b16, w.mha_t.wqkv_bf, w.mha_t.wqkv_tc, 2);
+    const void* wo_t = pick(w.mha_t.wo_f16, w.mha_t.wo_b16, w.mha_t.wo_bf, w.mha_t.wo_tc, 2);
+    const void* w1x = pick(w.w1_f16, w.w1_b16, w.w1_bf, w.w1_tc, 1);
+    const void* w2x = pick(w.w2_f16, w.w2_b16, w.w2_bf, w.w2_tc, 1);
     // residue attention (over L)
     TRY(ln_mod(h, s, h->h, h->xn, modm, off + 0, off + kC, N, rm_attn));
     TRY(gemm(h, s, EPI_STORE, h->xn, kC, w.mha_l.wqkv, wqkv_l, kC, N, kQKV, kC,
-             make_epi(w.mha_l.bqkv, h->qkv, kQKV, (h->emu_bf16 & 4) ? 2 : 0), "gemm_qkv", bf, bfq));
-    TRY(attention(h, s, h->qkv, c->mask, w.mha_l, h->att, sml, rm_attn, "mha_l", true, bfq));
+             make_epi(w.mha_l.bqkv, h->qkv, kQKV, (h->emu_bf16 & 4) ? 2 : 0), "gemm_qkv", hf, bfq));
+    TRY(attention(h, s, h->qkv, c->mask, w.mha_l, h->att, sml, rm_attn, "mha_l", true, hfq));
     TRY(gemm(h, s, EPI_RESID_GATE, h->att, kC, w.mha_l.wo, wo_l, kC, N, kC, kC,
-             make_epi_gate(w.mha_l.bo, h->h, kC, modm, off + 2 * kC), "gemm_out", bf));
+             make_epi_gate(w.mha_l.bo, h->h, kC, modm, off + 2 * kC), "gemm_out", hf));
     // time attention (over T)
     TRY(ln_mod(h, s, h->h, h->xn, modm, off + 3 * kC, off + 4 * kC, N, rm_attn));
     TRY(gemm(h, s, EPI_STORE, h->xn, kC, w.mha_t.wqkv, wqkv_t, kC, N, kQKV, kC,
-             make_epi(w.mha_t.bqkv, h->qkv, kQKV, (h->emu_bf16 & 4) ? 2 : 0), "gemm_qkv", bf, bfq));
-    TRY(attention(h, s, h->qkv, c->mask, w.mha_t, h->att, smt, rm_attn, "mha_t", true, bfq));
+             make_epi(w.mha_t.bqkv, h->qkv, kQKV, (h->emu_bf16 & 4) ? 2 : 0), "gemm_qkv", hf, bfq));
+    TRY(attention(h, s, h->qkv, c->mask, w.mha_t, h->att, smt, rm_attn, "mha_t", true, hfq));
     TRY(gemm(h, s, EPI_RESID_GATE, h->att, kC, w.mha_t.wo, wo_t, kC, N, kC, kC,
-             make_epi_gate(w.mha_t.bo, h->h, kC, modm, off + 5 * kC), "gemm_out", bf));
+             make_epi_gate(w.mha_t.bo, h->h, kC, modm, off + 5 * kC), "gemm_out", hf));
     // MLP (hidden activations are bf16 in bf16 mode: written by fc1, read only by fc2)
     TRY(ln_mod(h, s, h->h, h->xn, modm, off + 6 * kC, off + 7 * kC, N, rm_mlp));
     TRY(gemm(h, s, EPI_GELU, h->xn, kC, w.w1, w1x, kC, N, kFF, kC, make_epi(w.b1, h->hid, kFF, bf ? 0 : rm_mlp),
-             "gemm_fc1", bf, bf));
+             "gemm_fc1", hf, bf));
     TRY(gemm(h, s, EPI_RESID_GATE, h->hid, kFF, w.w2, w2x, kFF, N, kC, kFF,
-             make_epi_gate(w.b2, h->h, kC, modm, off + 8 * kC), "gemm_fc2", bf));
+             make_epi_gate(w.b2, h->h, kC, modm, off + 8 * kC), "gemm_fc2", hf));
   }
 
   // ---------------- final layer (+ Euler update)
@@ -769,11 +792,13 @@ static int finalize_weights_impl(mdgen_handle* h, cudaStream_t s) {
     TRY(tc_copy(h, s, w.w1, (size_t)kFF * kC, &w.w1_tc));
     TRY(tc_copy(h, s, w.w1, (size_t)kFF * kC, &w.w1_bf, 2));
     TRY(b16_copy(h, s, w.w1, (size_t)kFF * kC, &w.w1_b16));
+    TRY(f16_copy(h, s, w.w1, (size_t)kFF * kC, &w.w1_f16));
     TRY(pack_new(h, s, p + "fc1.bias", 1, kFF, &w.b1));
     TRY(pack_new(h, s, p + "fc2.weight", kC, kFF, &w.w2));
     TRY(tc_copy(h, s, w.w2, (size_t)kC * kFF, &w.w2_tc));
     TRY(tc_copy(h, s, w.w2, (size_t)kC * kFF, &w.w2_bf, 2));
     TRY(b16_copy(h, s, w.w2, (size_t)kC * kFF, &w.w2_b16));
+    TRY(f16_copy(h, s, w.w2, (size_t)kC * kFF, &w.w2_f16));
     TRY(pack_new(h, s, p + "fc2.bias", 1, kC, &w.b2));
   }
   {
@@ -1014,12 +1039,16 @@ int mdgen_debug_linear(mdgen_handle* h, const float* A, const float* W, const fl
   int mode = act ? EPI_GELU : EPI_STORE;
   if (use_tc) {
 #ifndef MDGEN_NO_TC
-    const bool bf = use_tc == 2;          // 2: bf16 operands (kind::f16), 1: TF32 operands
+    const bool bf = use_tc >= 2;          // 3: fp16 operands, 2: bf16 operands (kind::f16), 1: TF32 operands
+    ep.half_fmt = use_tc == 3 ? kFmtF16 : kFmtBF16;
     if (!tc_gemm_supported(N, K, bf)) { h->err = "shape unsupported by the tensor-core GEMM"; return MDGEN_E_INVALID; }
     float *Ar = nullptr, *Wr = nullptr;   // rounded operand copies (fp32 containers or bf16 arrays)
     TRY(dev_alloc_t(h, &Ar, (size_t)M * K));
     TRY(dev_alloc_t(h, &Wr, (size_t)N * K));
-    if (bf) {
+    if (use_tc == 3) {
+      to_f16_kernel<<<(unsigned)(((size_t)M * K + 255) / 256), 256, 0, s>>>(A, (uint16_t*)Ar, (long long)M * K);
+      to_f16_kernel<<<(unsigned)(((size_t)N * K + 255) / 256), 256, 0, s>>>(W, (uint16_t*)Wr, (long long)N * K);
+    } else if (bf) {
       to_bf16_kernel<<<(unsigned)(((size_t)M * K + 255) / 256), 256, 0, s>>>(A, (uint16_t*)Ar, (long long)M * K);
       to_bf16_kernel<<<(unsigned)(((size_t)N * K + 255) / 256), 256, 0, s>>>(W, (uint16_t*)Wr, (long long)N * K);
     } else {
@@ -1055,7 +1084,7 @@ int mdgen_set_option(mdgen_handle* h, const char* key, int64_t value) {
     h->use_tc = (int)value;
   } else if (k == "tc_min_rows") h->tc_min_rows = (int)value;
   else if (k == "use_tc_attn") h->use_tc_attn = (int)value;
-  else if (k == "attn_variant") h->attn_variant = (int)value & 255;
+  else if (k == "attn_variant") h->attn_variant = (int)value & 511;
   else if (k == "l4_variant") h->l4_variant = (int)value & 1;
   else if (k == "emu_bf16") h->emu_bf16 = (int)value;
   else if (k == "gemm_bf16") h->gemm_bf16 = (int)value;

@@ -16,7 +16,9 @@ TOL_SIMT = 1e-4     # fp32 SIMT validation kernels: re-association noise only
 TOL_GEOM = 2e-5     # prep / decode kernels are exact fp32 geometry
 
 
-PATHS = ["simt", "tf32", "bf16"]   # fp32 SIMT validation kernels | tcgen05 TF32 | tcgen05 bf16 GEMMs (default)
+# fp32 SIMT validation kernels | tcgen05 TF32 operands | tcgen05 bf16 operands | tcgen05 fp16 operands (default)
+PATHS = ["simt", "tf32", "bf16", "fp16"]
+GEMM_DTYPE = {"tf32": 0, "bf16": 1, "fp16": 2}
 
 
 def _wrapper(args, sd, path):
@@ -31,7 +33,7 @@ def _wrapper(args, sd, path):
     except MDGenError as e:
         pytest.skip(f"tensor-core kernels unavailable in this build: {e}")
     if path != "simt":
-        eng.set_option("gemm_bf16", 1 if path == "bf16" else 0)
+        eng.set_option("gemm_bf16", GEMM_DTYPE[path])
         # run the token GEMMs on the tensor cores even for the tiny test shapes; the IPA key-frame
         # trunk (<= 64 rows here) stays on its production fp32 path
         eng.set_option("tc_min_rows", 65)
@@ -140,16 +142,17 @@ def test_oracle_other_shapes(shape, path):
     assert rel_l2(xk.cpu(), xo) < tol
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 6, 14])
+@pytest.mark.parametrize("variant", [256, 257, 0, 1, 2, 3, 4, 6, 14])
 @pytest.mark.parametrize("shape", [(1, 300, 4, 4), (2, 40, 70, 3), (5, 300, 4, 2)])
 def test_attention_variants_match_oracle(shape, variant):
-    """Every build variant of the tcgen05 attention kernels (option `attn_variant`: bit 0 bf16 P.V, bit 1 staged
-    pre-pass, bit 2 persistent kernel, bit 3 persistent with 12 softmax warps; 3 is the default) against the
+    """Every build variant of the tcgen05 attention kernels (option `attn_variant`: 256 = generation 8, the
+    default, 257 = its 2-query-tile kernel forced; generation 7: bit 0 bf16 P.V, bit 1 staged
+    pre-pass, bit 2 persistent kernel, bit 3 persistent with 12 softmax warps) against the
     oracle: frame attention over 300 frames (3 query tiles, ragged key tiles; with B = 5 there are 960 work
     items, so every persistent CTA walks through several of them) and residue attention over 70 residues with
     padded (masked) keys."""
     args, sd, batch, zs, (_, xo) = _oracle_shape_case(shape)
-    m = _wrapper(args, sd, "bf16")
+    m = _wrapper(args, sd, "fp16" if variant >= 256 else "bf16")
     m.model.engine().set_option("attn_variant", variant)
     assert m.model.engine().get_option("attn_variant") == variant
     prep = m.prep_batch(_dev(batch))

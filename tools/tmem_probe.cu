@@ -189,6 +189,53 @@ int run_ld2(int num_sms, int warps, int ctas_per_sm, unsigned long long* d_cycle
   return 0;
 }
 
+
+// ---------------------------------------------------------------- part 5
+// What the softmax inner loop costs on the XU (MUFU) pipe: 2 x ex2 alone, + one cvt.rn.f16x2.f32 (F2FP.PACK_AB),
+// + one cvt.rn.bf16x2.f32, + a PRMT-based bf16 truncation pack, + FMNMX3 / FADD neighbours.
+template <int KIND>
+__global__ void __launch_bounds__(512) xu_mix_kernel(int reps, unsigned long long* cycles, uint32_t* sink) {
+  float x[8];
+  uint32_t acc = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) x[i] = -0.001f * (threadIdx.x + i);
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int r = 0; r < reps; ++r) {
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) {
+      float a, b;
+      asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(a) : "f"(x[i]));
+      asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(b) : "f"(x[i + 1]));
+      uint32_t pk = 0;
+      if (KIND == 1) asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(pk) : "f"(b), "f"(a));
+      if (KIND == 2) asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk) : "f"(b), "f"(a));
+      if (KIND == 3) asm volatile("prmt.b32 %0, %1, %2, 0x7632;" : "=r"(pk) : "r"(__float_as_uint(a)), "r"(__float_as_uint(b)));
+      if (KIND == 0) pk = __float_as_uint(a) ^ __float_as_uint(b);
+      acc += pk;
+      x[i] = -a; x[i + 1] = -b;
+    }
+  }
+  const long long t1 = clock64();
+  if (acc == 0x12345678u) sink[0] = acc;
+  if (threadIdx.x == 0) cycles[blockIdx.x] = (unsigned long long)(t1 - t0);
+}
+template <int KIND>
+int run_xu_mix(int num_sms, unsigned long long* d_cycles, uint32_t* d_sink) {
+  const int reps = 2048, grid = num_sms * 2;
+  xu_mix_kernel<KIND><<<grid, 512>>>(reps, d_cycles, d_sink);
+  CK(cudaDeviceSynchronize());
+  std::vector<unsigned long long> cyc(grid);
+  CK(cudaMemcpy(cyc.data(), d_cycles, grid * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  double mean = 0;
+  for (auto c : cyc) mean += (double)c;
+  mean /= grid;
+  const double exps_per_sm = 2.0 * 512 * reps * 8;
+  const char* nm[] = {"2 ex2 + xor                 ", "2 ex2 + cvt.rn.f16x2.f32    ", "2 ex2 + cvt.rn.bf16x2.f32   ", "2 ex2 + prmt (bf16 truncate)"};
+  printf("  %s: %6.2f exponentials/clk/SM  (%.0f cycles)\n", nm[KIND], exps_per_sm / mean, mean);
+  return 0;
+}
+
 // ---------------------------------------------------------------- part 2
 // D[128 x 32] = A[128 x 16] * B[32 x 16]^T with fp16 operands; A[i][k] = (k == i % 16), B[n][k] = n + 100 k
 // => D[i][n] = n + 100 (i % 16), exactly representable in fp16. c_format selects F16 (0) or F32 (1) accumulators.
@@ -319,6 +366,11 @@ int main() {
   if (run_ex2<0>(num_sms, d_cycles, d_sink)) return 1;
   if (run_ex2<1>(num_sms, d_cycles, d_sink)) return 1;
   if (run_ex2<2>(num_sms, d_cycles, d_sink)) return 1;
+  printf("part 5: XU pipe cost of the probability pack\n");
+  if (run_xu_mix<0>(num_sms, d_cycles, d_sink)) return 1;
+  if (run_xu_mix<1>(num_sms, d_cycles, d_sink)) return 1;
+  if (run_xu_mix<2>(num_sms, d_cycles, d_sink)) return 1;
+  if (run_xu_mix<3>(num_sms, d_cycles, d_sink)) return 1;
   printf("part 4: tcgen05.ld with two loads in flight per warp / tcgen05.st\n");
   for (int ctas = 1; ctas <= 2; ++ctas)
     for (int warps : {4, 8, 16}) {
