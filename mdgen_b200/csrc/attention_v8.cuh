@@ -1,5 +1,5 @@
 // tcgen05 fused attention, generation 8 (default for sequences longer than 64): softmax(Q K^T + key padding) V
-// with bias-KV token and RoPE (mdgen/model/mha.py:260-397), everything in fp16 operands / fp32 accumulation.
+// with bias-KV token and RoPE (mdgen/model/mha.py:260-397), fp16 operands / fp32 accumulation throughout.
 //
 // What changed against attention_tc.cuh (generation 7) and why (profiles/r2_attention_v8.md):
 //   * measured on B200 (tools/tmem_probe.cu): tcgen05.ld sustains 350-700 B/clk/SM, so the old kernel (45 B/clk/SM)
@@ -7,45 +7,52 @@
 //     mbarrier spin loops, per-CTA start-up) and by the 7.6 GB of key-tile images each launch pulled out of L2.
 //   * persistent CTAs, ONE per SM, each working on NQ = 4 query tiles (512 queries) of one (sequence, head) at
 //     a time against one shared K/V ring: a key-tile image is fetched from L2 once per 512 queries, not per 128.
-//   * one softmax thread per query row (FA4 style): no cross-warp exchange. Per 64-key tile a thread reads its
-//     64 fp32 scores from TMEM, takes the row maximum (FMNMX3), keeps its softmax reference unless the maximum
+//   * one softmax thread per query row (FA4 style): no cross-warp exchange. Per 48-key tile a thread reads its
+//     48 fp32 scores from TMEM, takes the row maximum (FMNMX3), keeps its softmax reference unless the maximum
 //     grew by more than 2^8 (lazy rescale of the O row in TMEM), exponentiates (MUFU ex2) and writes P back over
 //     the scores as fp16 pairs. Row sums come out of the P·V MMA itself (a row of ones in V^T), the key mask goes
 //     into the QK^T MMA (a mask column: masked keys score -30000), so the inner loop is 1 FADD + 1 MUFU + 1/2 F2FP
 //     + 1/2 FMNMX3 per score.
+//   * S is double buffered in TMEM and every query tile has its own MMA-issuing thread: QK^T of tile c+2 is issued
+//     right after P·V of tile c, so a softmax thread finds its next scores ready and no MMA / mbarrier round trip
+//     (measured: 500-1100 cycles each) sits on its critical path.
 //   * fp16 instead of TF32 / bf16 operands: Q, K (RoPE applied in fp32, then rounded once) and P, V carry TF32's
 //     11-bit significand at half the bytes; QK^T is 2 kind::f16 MMAs (K = 32 = 24 + mask column + padding)
-//     instead of 3 kind::tf32 ones, the key-tile image shrinks from 21 KB per 96 keys to 8 KB per 64 keys.
+//     instead of 3 kind::tf32 ones, P·V 3 instead of 6.
 //
-// Per (sequence, head, key tile of 64 keys) the pre-pass writes an 8 KB image:
-//   K   [64 keys x 32 halfs]  K-major SWIZZLE_64B   cols 0..23 = RoPE(k), col 25 = 1 for masked / out-of-range keys
-//   V^T [32 rows x 64 keys]   K-major SWIZZLE_128B  rows 0..23 = v^T, row 24 = 1 (row sums), rows 25..31 unused
+// The pre-pass writes, per (sequence, head, key tile of 48 keys), a 7 KB image
+//   K   [48 keys x 32 halfs]  K-major SWIZZLE_64B   cols 0..23 = RoPE(k), col 25 = 1 for masked / out-of-range keys
+//   V^T [32 rows x 64 keys]   K-major SWIZZLE_128B  rows 0..23 = v^T (keys 0..47), row 24 = 1 (row sums)
 // and, per 128 tokens of every (sequence, head), an 8 KB query-tile image
 //   Q   [128 rows x 32 halfs] K-major SWIZZLE_64B   cols 0..23 = RoPE(q) log2(e), col 25 = -30000 (masked-key offset)
 // Roles inside a CTA (NQ = 4: 21 warps; NQ = 2, used when the sequence has at most 256 queries: 11 warps, 2 CTAs/SM):
 //   warps [0, 4 NQ)      softmax + epilogue: warp w owns rows 32 (w & 3) .. +31 of query tile w >> 2
 //   1 warp               TMA producer (lane 0): cp.async.bulk of the item's query tiles into a double buffer and of
-//                        one K/V image per key tile into a 6-stage ring
+//                        one K/V image per key tile into an 8-stage ring
 //   NQ warps             MMA issuers (lane 0 each), one per query tile: S = Q K^T, O += P V
-// TMEM: 128 columns per query tile: S [0, 64), P [64, 96), O [96, 128) (N = 32: 24 head dims + row sum + padding).
+// TMEM per query tile (128 columns): S0 [0, 48), S1 [48, 96) (P overwrites the first 24 columns of its buffer),
+// O [96, 128) (N = 32: 24 head dims + row sum + padding).
 #pragma once
 #include "attention_tc.cuh"
 
 namespace mdgen {
 
-constexpr int A8_KT = 64;                        // keys per tile
-constexpr int A8_K_BYTES = A8_KT * 64;           // 4096: K block, 64-byte rows
-constexpr int A8_V_BYTES = 32 * 128;             // 4096: V^T block, one SWIZZLE_128B atom
-constexpr int A8_IMG = A8_K_BYTES + A8_V_BYTES;  // 8192
-constexpr int A8_STAGES = 6;
+constexpr int A8_KT = 48;                        // keys per tile
+constexpr int A8_K_BYTES = A8_KT * 64;           // 3072: K block, 64-byte rows
+constexpr int A8_V_BYTES = 32 * 128;             // 4096: V^T block, one SWIZZLE_128B atom (keys 48..63 unused)
+constexpr int A8_IMG = A8_K_BYTES + A8_V_BYTES;  // 7168
+constexpr int A8_STAGES = 8;
 constexpr int A8_QT_BYTES = 128 * 64;            // one staged query tile (128 rows x 64 B)
 constexpr float A8_MASKED = -30000.0f;           // score offset of a masked key (exp2 -> exactly 0)
+constexpr int A8_TSTRIDE = 128, A8_S1 = A8_KT, A8_OCOL = 96;   // TMEM columns: per query tile, S buffer 1, O
 constexpr float A8_LAZY = 8.0f;                  // the softmax reference moves only when the row maximum grows by > 2^8
 
 __host__ __device__ constexpr int a8_threads(int nq) { return (5 * nq + 1) * 32; }
 __host__ __device__ constexpr int a8_smem_bytes(int nq) {
   return 1024 /*align*/ + 2 * nq * A8_QT_BYTES + A8_STAGES * A8_IMG + 512 /*barriers*/;
 }
+__host__ __device__ inline int a8_nkt(int S) { return (S + 1 + A8_KT - 1) / A8_KT; }
+__host__ __device__ inline int a8_nqt_pad(int S) { return ((S + 511) / 512) * 4; }   // query tiles, padded to whole items
 
 // byte offset of 16-byte chunk `c` (0..3) of row `r` inside a [rows x 64 B] K-major SWIZZLE_64B tile
 // (Swizzle<2,4,3>: address bits [4,6) ^= bits [7,9), 512-byte atoms of 8 rows)
@@ -63,33 +70,16 @@ __device__ __forceinline__ uint64_t umma_desc_k64(uint32_t smem_addr) {
   return d;
 }
 
-// Non-suspending mbarrier poll (mbarrier.test_wait): for the few latency-critical single-thread waits of the MMA
-// issuers. try_wait parks the thread in hardware; measured on B200 inside this kernel, a parked thread sees an
-// arrival 500-1100 cycles late when ~20 warps of the CTA wait on barriers at the same time.
-__device__ __forceinline__ void mbar_spin(uint32_t bar, uint32_t parity) {
-  uint32_t ok = 0;
-  while (!ok) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  }
-}
-
 // ---------------------------------------------------------------------------------------------------------
-// Pre-pass: one block per (sequence, 64-token tile, head octet). The q|k|v row segments of the octet (3 x 384
-// contiguous bytes per token when q|k|v is 16-bit) are staged through shared memory with 16-byte cp.async, then
-// every thread builds the image rows of two (head, token) pairs: the K row and V^T column of the token as a key,
+// Pre-pass: one block per (sequence, 48-token tile, head octet), 384 threads = one (head, token) pair each. The
+// q|k|v row segments of the octet (3 x 384 contiguous bytes per token when q|k|v is 16-bit) are staged through
+// shared memory with 16-byte cp.async; every thread then builds the K row and V^T column of its token as a key,
 // and its row of the Q image as a query (RoPE, x log2 e, fp16; col 25 = the masked-key score offset).
-// Scratch layout: [num_seq * 16 * nkt key-tile images (8 KB)] [num_seq * 16 * nqt_pad query-tile images (8 KB)].
+// Scratch layout: [num_seq * 16 * nkt key-tile images (7 KB)] [num_seq * 16 * nqt_pad query-tile images (8 KB)].
 constexpr int A8P_PITCH = 1168;                  // staged row: 3 x 384 B + 16 (bank spread)
 constexpr int A8P_SMEM = A8_KT * A8P_PITCH;
-__host__ __device__ inline int a8_nkt(int S) { return (S + 1 + A8_KT - 1) / A8_KT; }
-__host__ __device__ inline int a8_nqt_pad(int S) { return ((S + 511) / 512) * 4; }   // query tiles, padded to whole items
-__global__ void __launch_bounds__(256) attn8_prep_kernel(AttnParams p, uint8_t* __restrict__ scratch) {
+constexpr int A8P_THREADS = 8 * A8_KT;           // 384
+__global__ void __launch_bounds__(A8P_THREADS, 2) attn8_prep_kernel(AttnParams p, uint8_t* __restrict__ scratch) {
   extern __shared__ __align__(16) uint8_t a8p_smem[];
   const SeqMap& sm = p.sm;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -102,7 +92,7 @@ __global__ void __launch_bounds__(256) attn8_prep_kernel(AttnParams p, uint8_t* 
   const bool half_in = p.qkv_fmt != kFmtF32;
   if (half_in) {
     const uint16_t* qkv = reinterpret_cast<const uint16_t*>(p.qkv);
-    for (int row = warp; row < A8_KT; row += 8) {
+    for (int row = warp; row < A8_KT; row += A8P_THREADS / 32) {
       const int j = kt * A8_KT + row;
       if (j < S) {
         const long long tk = seq_token(sm, s, j);
@@ -116,124 +106,110 @@ __global__ void __launch_bounds__(256) attn8_prep_kernel(AttnParams p, uint8_t* 
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
   }
-#pragma unroll 1
-  for (int it = 0; it < 2; ++it) {
-    const int item = it * 256 + tid;
-    const int hl = item >> 6, r = item & 63;     // a warp = one head x 32 consecutive tokens
-    const int h = hg * 8 + hl;
-    const int j = kt * A8_KT + r;
-    uint8_t* kbase = scratch + ((size_t)(s * kH + h) * nkt + kt) * A8_IMG;
-    uint8_t* vbase = kbase + A8_K_BYTES;
-    float k[kHD], v[kHD];
-    float masked = 0.f;
-    if (j < S) {
-      const long long tk = seq_token(sm, s, j);
-      float q[kHD];
-      if (half_in) {
-        const uint8_t* rowp = a8p_smem + r * A8P_PITCH + hl * 48;
+  const int hl = tid / A8_KT, r = tid - hl * A8_KT;
+  const int h = hg * 8 + hl;
+  const int j = kt * A8_KT + r;
+  uint8_t* kbase = scratch + ((size_t)(s * kH + h) * nkt + kt) * A8_IMG;
+  uint8_t* vbase = kbase + A8_K_BYTES;
+  float k[kHD], v[kHD];
+  float masked = 0.f;
+  if (j < S) {
+    const long long tk = seq_token(sm, s, j);
+    float q[kHD];
+    if (half_in) {
+      const uint8_t* rowp = a8p_smem + r * A8P_PITCH + hl * 48;
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          const uint4 uq = *reinterpret_cast<const uint4*>(rowp + i * 16);
-          const uint4 uk = *reinterpret_cast<const uint4*>(rowp + 384 + i * 16);
-          const uint4 uv = *reinterpret_cast<const uint4*>(rowp + 768 + i * 16);
-          const uint32_t wq[4] = {uq.x, uq.y, uq.z, uq.w}, wk[4] = {uk.x, uk.y, uk.z, uk.w}, wv[4] = {uv.x, uv.y, uv.z, uv.w};
+      for (int i = 0; i < 3; ++i) {
+        const uint4 uq = *reinterpret_cast<const uint4*>(rowp + i * 16);
+        const uint4 uk = *reinterpret_cast<const uint4*>(rowp + 384 + i * 16);
+        const uint4 uv = *reinterpret_cast<const uint4*>(rowp + 768 + i * 16);
+        const uint32_t wq[4] = {uq.x, uq.y, uq.z, uq.w}, wk[4] = {uk.x, uk.y, uk.z, uk.w}, wv[4] = {uv.x, uv.y, uv.z, uv.w};
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const float2 fq = unpack_half2(wq[c], p.qkv_fmt), fk = unpack_half2(wk[c], p.qkv_fmt), fv = unpack_half2(wv[c], p.qkv_fmt);
-            q[8 * i + 2 * c] = fq.x; q[8 * i + 2 * c + 1] = fq.y;
-            k[8 * i + 2 * c] = fk.x; k[8 * i + 2 * c + 1] = fk.y;
-            v[8 * i + 2 * c] = fv.x; v[8 * i + 2 * c + 1] = fv.y;
-          }
+        for (int c = 0; c < 4; ++c) {
+          const float2 fq = unpack_half2(wq[c], p.qkv_fmt), fk = unpack_half2(wk[c], p.qkv_fmt), fv = unpack_half2(wv[c], p.qkv_fmt);
+          q[8 * i + 2 * c] = fq.x; q[8 * i + 2 * c + 1] = fq.y;
+          k[8 * i + 2 * c] = fk.x; k[8 * i + 2 * c + 1] = fk.y;
+          v[8 * i + 2 * c] = fv.x; v[8 * i + 2 * c + 1] = fv.y;
         }
-      } else {
-        load24(p.qkv, (size_t)tk * kQKV + h * kHD, kFmtF32, q);
-        load24(p.qkv, (size_t)tk * kQKV + kC + h * kHD, kFmtF32, k);
-        load24(p.qkv, (size_t)tk * kQKV + 2 * kC + h * kHD, kFmtF32, v);
       }
-      if (p.mask && p.mask[tk] == 0.f) masked = 1.f;
-      // ---- this token as a query: row (j & 127) of query tile (j >> 7)
-      rope24(q, p.cosT + j * kHalf, p.sinT + j * kHalf);
-      uint8_t* qdst = qimg0 + ((size_t)(s * kH + h) * nqt + (j >> 7)) * A8_QT_BYTES;
-      const int qr = j & 127;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        uint4 w;
-        w.x = pack_f16x2_rn(q[8 * c] * 1.4426950408889634f, q[8 * c + 1] * 1.4426950408889634f);
-        w.y = pack_f16x2_rn(q[8 * c + 2] * 1.4426950408889634f, q[8 * c + 3] * 1.4426950408889634f);
-        w.z = pack_f16x2_rn(q[8 * c + 4] * 1.4426950408889634f, q[8 * c + 5] * 1.4426950408889634f);
-        w.w = pack_f16x2_rn(q[8 * c + 6] * 1.4426950408889634f, q[8 * c + 7] * 1.4426950408889634f);
-        *reinterpret_cast<uint4*>(qdst + sw64_off(qr, c)) = w;
-      }
-      *reinterpret_cast<uint4*>(qdst + sw64_off(qr, 3)) = make_uint4(pack_f16x2_rn(0.f, A8_MASKED), 0u, 0u, 0u);
-    } else if (j == S) {
-#pragma unroll
-      for (int i = 0; i < kHD; ++i) { k[i] = p.bias_k[h * kHD + i]; v[i] = p.bias_v[h * kHD + i]; }
     } else {
-#pragma unroll
-      for (int i = 0; i < kHD; ++i) { k[i] = 0.f; v[i] = 0.f; }
-      masked = 1.f;
+      load24(p.qkv, (size_t)tk * kQKV + h * kHD, kFmtF32, q);
+      load24(p.qkv, (size_t)tk * kQKV + kC + h * kHD, kFmtF32, k);
+      load24(p.qkv, (size_t)tk * kQKV + 2 * kC + h * kHD, kFmtF32, v);
     }
-    if (j <= S) rope24(k, p.cosT + j * kHalf, p.sinT + j * kHalf);
-    // K row: 24 halfs | col 24 = 0 | col 25 = mask flag | zeros
+    if (p.mask && p.mask[tk] == 0.f) masked = 1.f;
+    // ---- this token as a query: row (j & 127) of query tile (j >> 7)
+    rope24(q, p.cosT + j * kHalf, p.sinT + j * kHalf);
+    uint8_t* qdst = qimg0 + ((size_t)(s * kH + h) * nqt + (j >> 7)) * A8_QT_BYTES;
+    const int qr = j & 127;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       uint4 w;
-      w.x = pack_f16x2_rn(k[8 * c], k[8 * c + 1]); w.y = pack_f16x2_rn(k[8 * c + 2], k[8 * c + 3]);
-      w.z = pack_f16x2_rn(k[8 * c + 4], k[8 * c + 5]); w.w = pack_f16x2_rn(k[8 * c + 6], k[8 * c + 7]);
-      *reinterpret_cast<uint4*>(kbase + sw64_off(r, c)) = w;
+      w.x = pack_f16x2_rn(q[8 * c] * 1.4426950408889634f, q[8 * c + 1] * 1.4426950408889634f);
+      w.y = pack_f16x2_rn(q[8 * c + 2] * 1.4426950408889634f, q[8 * c + 3] * 1.4426950408889634f);
+      w.z = pack_f16x2_rn(q[8 * c + 4] * 1.4426950408889634f, q[8 * c + 5] * 1.4426950408889634f);
+      w.w = pack_f16x2_rn(q[8 * c + 6] * 1.4426950408889634f, q[8 * c + 7] * 1.4426950408889634f);
+      *reinterpret_cast<uint4*>(qdst + sw64_off(qr, c)) = w;
     }
-    *reinterpret_cast<uint4*>(kbase + sw64_off(r, 3)) = make_uint4(pack_f16x2_rn(0.f, masked), 0u, 0u, 0u);
-    // V^T: element (d, key r) at row d, 16-byte chunk r >> 3, half r & 7; row 24 = 1
-    const int kc = r >> 3, kw = r & 7;
+    *reinterpret_cast<uint4*>(qdst + sw64_off(qr, 3)) = make_uint4(pack_f16x2_rn(0.f, A8_MASKED), 0u, 0u, 0u);
+  } else if (j == S) {
 #pragma unroll
-    for (int d = 0; d < kHD; ++d)
-      reinterpret_cast<uint16_t*>(vbase + sw128_off(d, kc))[kw] = (uint16_t)(pack_f16x2_rn(v[d], 0.f) & 0xFFFFu);
-    reinterpret_cast<uint16_t*>(vbase + sw128_off(24, kc))[kw] = 0x3C00u;   // fp16 1.0
+    for (int i = 0; i < kHD; ++i) { k[i] = p.bias_k[h * kHD + i]; v[i] = p.bias_v[h * kHD + i]; }
+  } else {
+#pragma unroll
+    for (int i = 0; i < kHD; ++i) { k[i] = 0.f; v[i] = 0.f; }
+    masked = 1.f;
   }
+  if (j <= S) rope24(k, p.cosT + j * kHalf, p.sinT + j * kHalf);
+  // K row: 24 halfs | col 24 = 0 | col 25 = mask flag | zeros
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    uint4 w;
+    w.x = pack_f16x2_rn(k[8 * c], k[8 * c + 1]); w.y = pack_f16x2_rn(k[8 * c + 2], k[8 * c + 3]);
+    w.z = pack_f16x2_rn(k[8 * c + 4], k[8 * c + 5]); w.w = pack_f16x2_rn(k[8 * c + 6], k[8 * c + 7]);
+    *reinterpret_cast<uint4*>(kbase + sw64_off(r, c)) = w;
+  }
+  *reinterpret_cast<uint4*>(kbase + sw64_off(r, 3)) = make_uint4(pack_f16x2_rn(0.f, masked), 0u, 0u, 0u);
+  // V^T: element (d, key r) at row d, 16-byte chunk r >> 3, half r & 7; row 24 = 1
+  const int kc = r >> 3, kw = r & 7;
+#pragma unroll
+  for (int d = 0; d < kHD; ++d)
+    reinterpret_cast<uint16_t*>(vbase + sw128_off(d, kc))[kw] = (uint16_t)(pack_f16x2_rn(v[d], 0.f) & 0xFFFFu);
+  reinterpret_cast<uint16_t*>(vbase + sw128_off(24, kc))[kw] = 0x3C00u;   // fp16 1.0
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// TMEM per query tile t (128 columns at t * 128): S [0, 64) fp32 scores | P [64, 96) fp16 probability pairs |
-// O [96, 128) fp32 (24 head dims, row sum, padding). S and P are separate so that the next key tile's QK^T can be
-// issued as soon as the softmax threads have READ the current scores (they keep them in registers): the tensor
-// work of tile c+1 overlaps the exponentials of tile c and a softmax thread never waits for an MMA round trip.
-// Every query tile has its own MMA-issuing thread, so the NQ tiles of a CTA run fully decoupled (they only share
-// the K/V ring) and drift out of phase, which keeps the MUFU pipe fed while one tile reads or writes TMEM.
-// mbarriers per query tile: s_full (QK^T done) -> s_read (4 warps hold S in registers) -> QK^T of the next tile;
-// p_ready (4 warps wrote P) -> P·V -> p_free (P and O may be touched again); o_done / o_free once per item.
-#define A8_WAIT(bar, par) do { if (SPIN) mbar_spin(bar, par); else mbar_wait(bar, par); } while (0)
-template <int NQ, bool USE_TURN, bool SPIN>
+// mbarriers per query tile t: s_full[t][b] (QK^T into S buffer b done) -> softmax; p_ready[t][b] (4 warps wrote
+// P over buffer b) -> P·V -> pv_done[t][b] (O includes that tile);
+// o_free[t] once per item (epilogue has read O). Shared: kv_full / kv_free per ring stage (kv_free counts the NQ
+// issuers), q_full / q_free per query double buffer.
+template <int NQ>
 __global__ void __launch_bounds__(a8_threads(NQ), NQ == 4 ? 1 : 2) attn8_kernel(AttnParams p, const uint8_t* __restrict__ scratch,
-                                                                            int total_items, int nqi /*items per (seq, head)*/,
-                                                                            unsigned long long* __restrict__ dbg /*phase timers or null*/) {
+                                                                            int total_items, int nqi /*items per (seq, head)*/) {
   constexpr int NSW = 4 * NQ;                    // softmax warps
   constexpr int W_TMA = NSW, W_MMA = NSW + 1;    // producer warp, first of the NQ MMA-issuer warps
   constexpr int QROWS = NQ * 128;                // queries per item
-  constexpr int TMEM_COLS = NQ * 128;
+  constexpr int TMEM_COLS = NQ * A8_TSTRIDE;
   extern __shared__ uint8_t smem_raw[];
   const SeqMap& sm = p.sm;
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t sbase = (raw + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - raw);
   const uint32_t q_off = 0;                                        // [2 buffers][NQ tiles][128 rows x 64 B]
-  const uint32_t st_off = 2 * NQ * A8_QT_BYTES;                    // stage: [K 4096 | V^T 4096]
+  const uint32_t st_off = 2 * NQ * A8_QT_BYTES;                    // stage: [K 3072 | V^T 4096]
   const uint32_t bar_off = st_off + A8_STAGES * A8_IMG;
-  auto b_sfull = [&](int t) { return sbase + bar_off + 8 * t; };                       // [NQ] QK^T -> softmax
-  auto b_sread = [&](int t) { return sbase + bar_off + 32 + 8 * t; };                  // [NQ] softmax -> MMA issuer
-  auto b_pready = [&](int t) { return sbase + bar_off + 64 + 8 * t; };                 // [NQ] softmax -> MMA issuer
-  auto b_pfree = [&](int t) { return sbase + bar_off + 96 + 8 * t; };                  // [NQ] P·V retired -> softmax
-  auto b_odone = [&](int t) { return sbase + bar_off + 128 + 8 * t; };                 // [NQ] item's O complete -> epilogue
-  auto b_ofree = [&](int t) { return sbase + bar_off + 160 + 8 * t; };                 // [NQ] epilogue -> MMA issuer
-  auto b_kvfull = [&](int s) { return sbase + bar_off + 192 + 8 * s; };                // [6] TMA -> MMA issuers
-  auto b_kvfree = [&](int s) { return sbase + bar_off + 240 + 8 * s; };                // [6] P·V of all NQ tiles retired -> TMA
-  auto b_qfull = [&](int b) { return sbase + bar_off + 288 + 8 * b; };                 // [2] TMA -> MMA issuers
-  auto b_qfree = [&](int b) { return sbase + bar_off + 304 + 8 * b; };                 // [2] QK^T of all NQ tiles retired -> TMA
-  // MUFU turn tokens: the NQ softmax warps that share an SM sub-partition (same lane quarter qq, one per query
-  // tile) exponentiate in round-robin order, at most ~2 at a time (a warp passes the token on after the first
-  // half of its tile). Without it the warps fall into a convoy: all in the MUFU phase together, then all waiting
-  // on TMEM / barriers together, and the MUFU pipe sits idle half of the time.
-  auto b_turn = [&](int qq, int t) { return sbase + bar_off + 328 + 8 * (qq * NQ + t); };   // [4][NQ]
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sgen + bar_off + 320);
+  auto b_sfull = [&](int t, int b) { return sbase + bar_off + 8 * (2 * t + b); };            // [NQ][2]
+  auto b_pready = [&](int t, int b) { return sbase + bar_off + 64 + 8 * (2 * t + b); };      // [NQ][2]
+  // P·V-done barriers, one per key-tile parity: with S double buffered a softmax warp may finish tile c before
+  // P·V(c-1) retires, so a single barrier advancing once per tile would let a parity wait for tile c pass while
+  // tile c-1 is still pending (the waiter must never be more than one phase behind)
+  auto b_pvdone = [&](int t, int b) { return sbase + bar_off + 128 + 8 * (2 * t + b); };     // [NQ][2]
+  auto b_ofree = [&](int t) { return sbase + bar_off + 192 + 8 * t; };                       // [NQ]
+  auto b_kvfull = [&](int s) { return sbase + bar_off + 224 + 8 * s; };                      // [8]
+  auto b_kvfree = [&](int s) { return sbase + bar_off + 288 + 8 * s; };                      // [8]
+  auto b_qfull = [&](int b) { return sbase + bar_off + 352 + 8 * b; };                       // [2]
+  auto b_qfree = [&](int b) { return sbase + bar_off + 368 + 8 * b; };                       // [2]
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sgen + bar_off + 384);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int S = sm.S;
@@ -244,15 +220,12 @@ __global__ void __launch_bounds__(a8_threads(NQ), NQ == 4 ? 1 : 2) attn8_kernel(
 
   if (tid == 0) {
     for (int t = 0; t < NQ; ++t) {
-      mbar_init(b_sfull(t), 1); mbar_init(b_sread(t), 4); mbar_init(b_pready(t), 4); mbar_init(b_pfree(t), 1);
-      mbar_init(b_odone(t), 1); mbar_init(b_ofree(t), 4);
+      for (int b = 0; b < 2; ++b) { mbar_init(b_sfull(t, b), 1); mbar_init(b_pready(t, b), 4); mbar_init(b_pvdone(t, b), 1); }
+      mbar_init(b_ofree(t), 4);
     }
     for (int i = 0; i < A8_STAGES; ++i) { mbar_init(b_kvfull(i), 1); mbar_init(b_kvfree(i), NQ); }
     for (int b = 0; b < 2; ++b) { mbar_init(b_qfull(b), 1); mbar_init(b_qfree(b), NQ); }
-    for (int k = 0; k < 4; ++k)
-      for (int t = 0; t < NQ; ++t) mbar_init(b_turn(k, t), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    for (int k = 0; k < 4; ++k) mbar_arrive(b_turn(k, 0));      // query tile 0 owns the first turn
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
@@ -300,137 +273,82 @@ __global__ void __launch_bounds__(a8_threads(NQ), NQ == 4 ? 1 : 2) attn8_kernel(
         }
       }
     }
-  } else if (warp >= W_MMA && warp < W_MMA + NQ) {
+  } else if (warp >= W_MMA) {
     if (lane == 0) {
       // =============================== MMA issuer of query tile t ===============================
-      // program order: QK^T(0); for every tile c: QK^T(c+1) as soon as S(c) has been read, then P·V(c)
+      // program order: QK^T(0), QK^T(1); for every tile c: P·V(c), then QK^T(c+2) into the buffer P(c) occupied
       const int t = warp - W_MMA;
       constexpr uint32_t idesc_qk = umma_idesc_f16(128, A8_KT);
       constexpr uint32_t idesc_pv = umma_idesc_f16(128, 32);
-      const uint32_t tT = tmem_base + t * 128;
-      // issuer timers (dbg != null): 0 wait q_full, 1 wait kv_full, 2 wait s_read, 3 issue QK, 4 wait p_ready, 5 wait o_free + issue PV
-      long long mph[6] = {0, 0, 0, 0, 0, 0}, mk0 = 0;
-#define A8_MTICK(ph) do { if (dbg) { const long long now_ = clock64(); mph[ph] += now_ - mk0; mk0 = now_; } } while (0)
-      if (dbg) mk0 = clock64();
-      unsigned long long* trace = (dbg && bid == 0 && t == 0) ? dbg + (size_t)nblk * 5 * NQ * 6 : nullptr;   // [64 tiles][8 stamps]
-      auto issue_qk = [&](int c, int i, int g) {
-        const int qb = i & 1, st = c % A8_STAGES;
-        if (g == 0) mbar_wait(b_qfull(qb), (uint32_t)((i >> 1) & 1));
-        A8_MTICK(0);
-        mbar_wait(b_kvfull(st), (uint32_t)((c / A8_STAGES) & 1));
-        A8_MTICK(1);
-        if (c > 0) A8_WAIT(b_sread(t), (uint32_t)((c - 1) & 1));         // the scores of tile c-1 are in registers
-        if (trace && c >= 1 && c <= 64) trace[(c - 1) * 8 + 4] = clock64();      // s_read(c-1) observed by the issuer
-        A8_MTICK(2);
+      const uint32_t tT = tmem_base + t * A8_TSTRIDE;
+      int qk_c = 0, qk_i = 0, qk_g = 0;             // cursor of the next QK^T (tile, item, tile-in-item)
+      auto issue_qk = [&]() {
+        const int qb = qk_i & 1, st = qk_c % A8_STAGES;
+        if (qk_g == 0) mbar_wait(b_qfull(qb), (uint32_t)((qk_i >> 1) & 1));
+        mbar_wait(b_kvfull(st), (uint32_t)((qk_c / A8_STAGES) & 1));
         tc_fence_after();
         const uint64_t kdesc = umma_desc_k64(sbase + st_off + st * A8_IMG);
         const uint64_t qdesc = umma_desc_k64(sbase + q_off + (qb * NQ + t) * A8_QT_BYTES);
-        tc_mma_bf16(tT, qdesc, kdesc, idesc_qk, 0u);
-        tc_mma_bf16(tT, qdesc + 2, kdesc + 2, idesc_qk, 1u);
-        tc_commit(b_sfull(t));
-        if (g == nkt - 1) tc_commit(b_qfree(qb));                        // this tile's last QK^T of the item
-        if (trace && c >= 1 && c <= 64) trace[(c - 1) * 8 + 5] = clock64();      // QK(c) issued
-        A8_MTICK(3);
+        const uint32_t tS = tT + (qk_c & 1) * A8_S1;
+        tc_mma_bf16(tS, qdesc, kdesc, idesc_qk, 0u);
+        tc_mma_bf16(tS, qdesc + 2, kdesc + 2, idesc_qk, 1u);
+        tc_commit(b_sfull(t, qk_c & 1));
+        if (qk_g == nkt - 1) tc_commit(b_qfree(qb));                     // this tile's last QK^T of the item
+        ++qk_c;
+        if (++qk_g == nkt) { qk_g = 0; ++qk_i; }
       };
-      int i = 0, g = 0;          // item / tile-in-item of tile c
-      int in = 0, gn = 0;        // ... of tile c + 1
-      if (ttot > 0) {
-        issue_qk(0, 0, 0);
-        if (++gn == nkt) { gn = 0; ++in; }
-      }
+      if (ttot > 0) issue_qk();
+      if (ttot > 1) issue_qk();
+      int i = 0, g = 0;
       for (int c = 0; c < ttot; ++c) {
-        if (c + 1 < ttot) {
-          issue_qk(c + 1, in, gn);
-          if (++gn == nkt) { gn = 0; ++in; }
-        }
-        const int st = c % A8_STAGES;
-        A8_WAIT(b_pready(t), (uint32_t)(c & 1));                                 // the 4 warps of this tile wrote P(c)
-        if (trace && c < 64) trace[c * 8 + 6] = clock64();                       // p_ready(c) observed by the issuer
-        A8_MTICK(4);
+        const int st = c % A8_STAGES, buf = c & 1;
+        mbar_wait(b_pready(t, buf), (uint32_t)((c >> 1) & 1));                   // the 4 warps of this tile wrote P(c)
         if (g == 0 && i > 0) mbar_wait(b_ofree(t), (uint32_t)((i - 1) & 1));     // previous item's O has been read
         tc_fence_after();
         const uint64_t vdesc = umma_desc_k128(sbase + st_off + st * A8_IMG + A8_K_BYTES);
+        const uint32_t tP = tT + buf * A8_S1;
 #pragma unroll
         for (int ks = 0; ks < A8_KT / 16; ++ks)
-          tc_mma_bf16_ts(tT + 96, tT + 64 + 8 * ks, vdesc + (uint64_t)(2 * ks), idesc_pv, (uint32_t)((g | ks) != 0));
-        tc_commit(b_pfree(t));
+          tc_mma_bf16_ts(tT + A8_OCOL, tP + 8 * ks, vdesc + (uint64_t)(2 * ks), idesc_pv, (uint32_t)((g | ks) != 0));
+        tc_commit(b_pvdone(t, buf));
         tc_commit(b_kvfree(st));                                                 // this tile is done with the stage
-        if (g == nkt - 1) tc_commit(b_odone(t));                                 // the item's O(t) is complete
-        if (trace && c < 64) trace[c * 8 + 7] = clock64();                       // PV(c) issued
-        A8_MTICK(5);
+        if (c + 2 < ttot) issue_qk();                                            // refill this S buffer (in order after P·V(c))
         if (++g == nkt) { g = 0; ++i; }
       }
-      if (dbg) {
-#pragma unroll
-        for (int k = 0; k < 6; ++k) dbg[((size_t)nblk * NSW + (size_t)bid * NQ + t) * 6 + k] = (unsigned long long)mph[k];
-      }
-#undef A8_MTICK
     }
-  } else if (warp < NSW) {
+  } else {
     // =============================== softmax + epilogue: one thread per query row ===============================
     const int t = warp >> 2, qq = warp & 3;
     const int row = qq * 32 + lane;
-    const uint32_t tS = tmem_base + t * 128 + ((uint32_t)(qq * 32) << 16);
-    const uint32_t tP = tS + 64, tO = tS + 96;
+    const uint32_t tT = tmem_base + t * A8_TSTRIDE + ((uint32_t)(qq * 32) << 16);
+    const uint32_t tO = tT + A8_OCOL;
     int c = 0;
-    // phase timers (dbg != null): 0 wait s_full, 1 TMEM load, 2 max + exp + pack, 3 wait p_free, 4 store P + arrive, 5 epilogue
-    long long tph[6] = {0, 0, 0, 0, 0, 0}, tk0 = 0;
-    unsigned long long* trace = (dbg && bid == 0 && warp == 0 && lane == 0) ? dbg + (size_t)nblk * 5 * NQ * 6 : nullptr;
-#define A8_TICK(ph) do { if (dbg) { const long long now_ = clock64(); tph[ph] += now_ - tk0; tk0 = now_; } } while (0)
-    if (dbg) tk0 = clock64();
     for (int i = 0; i < n_my; ++i) {
-      const int item = bid + i * nblk;
-      const int qi = item % nqi;
-      const long long sh = item / nqi;
-      const int h = (int)(sh % kH);
-      const long long s = sh / kH;
-      const int e = qi * QROWS + t * 128 + row;
       float m_ref = -INFINITY;
       for (int g = 0; g < nkt; ++g, ++c) {
-        A8_WAIT(b_sfull(t), (uint32_t)(c & 1));
+        const int buf = c & 1;
+        const uint32_t tS = tT + buf * A8_S1;
+        mbar_wait(b_sfull(t, buf), (uint32_t)((c >> 1) & 1));
         tc_fence_after();
-        if (trace && c < 64) trace[c * 8 + 0] = clock64();       // s_full(c) observed
-        A8_TICK(0);
-        uint32_t va[32], vb[32];
+        uint32_t va[32], vb[16];
         tc_ld32(tS, va);
-        tc_ld32(tS + 32, vb);
+        tc_ld16(tS + 32, vb);
         tc_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(b_sread(t));            // S may be overwritten by the next tile's QK^T
-        if (trace && c < 64) trace[c * 8 + 1] = clock64();       // s_read(c) arrived
-        A8_TICK(1);
-        // ---- row maximum of the 64 scores (two independent chains)
-        float mx0 = fmaxf(__uint_as_float(va[0]), __uint_as_float(vb[0])), mx1 = fmaxf(__uint_as_float(va[1]), __uint_as_float(vb[1]));
+        // ---- row maximum of the 48 scores (two independent chains)
+        float mx0 = fmaxf(__uint_as_float(va[0]), __uint_as_float(va[1])), mx1 = fmaxf(__uint_as_float(vb[0]), __uint_as_float(vb[1]));
 #pragma unroll
-        for (int k = 2; k < 32; k += 2) {
-          mx0 = fmaxf(mx0, fmaxf(__uint_as_float(va[k]), __uint_as_float(vb[k])));
-          mx1 = fmaxf(mx1, fmaxf(__uint_as_float(va[k + 1]), __uint_as_float(vb[k + 1])));
-        }
+        for (int k = 2; k < 32; k += 2) mx0 = fmaxf(mx0, fmaxf(__uint_as_float(va[k]), __uint_as_float(va[k + 1])));
+#pragma unroll
+        for (int k = 2; k < 16; k += 2) mx1 = fmaxf(mx1, fmaxf(__uint_as_float(vb[k]), __uint_as_float(vb[k + 1])));
         const float tmax = fmaxf(mx0, mx1);
         // ---- lazy reference: keep it unless the maximum outgrew it by more than 2^A8_LAZY (P stays <= 2^8: fp16 safe)
         const bool move = tmax > m_ref + A8_LAZY;          // always true on the first tile (m_ref = -inf)
         const float m_new = move ? tmax : m_ref;
-        // ---- P = exp2(S - m_ref) as fp16 pairs (in the score registers), in this warp's MUFU turn
-        if (USE_TURN) mbar_wait(b_turn(qq, t), (uint32_t)(c & 1));
-#pragma unroll
-        for (int k = 0; k < 16; ++k)
-          va[k] = pack_f16x2_rn(ex2f(__uint_as_float(va[2 * k]) - m_new), ex2f(__uint_as_float(va[2 * k + 1]) - m_new));
-        if (USE_TURN) {
-          __syncwarp();
-          if (lane == 0) mbar_arrive(b_turn(qq, t + 1 == NQ ? 0 : t + 1));
-        }
-#pragma unroll
-        for (int k = 0; k < 16; ++k)
-          va[16 + k] = pack_f16x2_rn(ex2f(__uint_as_float(vb[2 * k]) - m_new), ex2f(__uint_as_float(vb[2 * k + 1]) - m_new));
-        if (trace && c < 64) trace[c * 8 + 2] = clock64();       // exps done
-        A8_TICK(2);
-        // ---- P·V of the previous tile has retired: P and O may be touched
-        if (c > 0) A8_WAIT(b_pfree(t), (uint32_t)((c - 1) & 1));
-        tc_fence_after();
-        A8_TICK(3);
         if (g > 0 && __any_sync(0xffffffffu, move)) {
-          // the reference of some row moved: rescale this thread's O row (all 32 columns: head dims + row sum)
+          // the reference of some row moved: rescale this thread's O row (all 32 columns: head dims + row sum),
+          // once P·V of the previous tile has retired
+          mbar_wait(b_pvdone(t, (c - 1) & 1), (uint32_t)(((c - 1) >> 1) & 1));
+          tc_fence_after();
           const float alpha = move ? ex2f(m_ref - m_new) : 1.0f;
 #pragma unroll 1
           for (int cb = 0; cb < 32; cb += 8) {
@@ -443,16 +361,29 @@ __global__ void __launch_bounds__(a8_threads(NQ), NQ == 4 ? 1 : 2) attn8_kernel(
           }
         }
         m_ref = m_new;
-        tc_st32(tP, va);
+        // ---- P = exp2(S - m_ref) as fp16 pairs (in the score registers), stored over the first 24 score columns
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+          va[k] = pack_f16x2_rn(ex2f(__uint_as_float(va[2 * k]) - m_new), ex2f(__uint_as_float(va[2 * k + 1]) - m_new));
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          vb[k] = pack_f16x2_rn(ex2f(__uint_as_float(vb[2 * k]) - m_new), ex2f(__uint_as_float(vb[2 * k + 1]) - m_new));
+        {
+          uint32_t p0[16], p1[8];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) p0[k] = va[k];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) p1[k] = vb[k];
+          tc_st16(tS, p0);
+          tc_st8(tS + 16, p1);
+        }
         tc_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(b_pready(t));
-        if (trace && c < 64) trace[c * 8 + 3] = clock64();       // p_ready(c) arrived
-        A8_TICK(4);
+        if (lane == 0) mbar_arrive(b_pready(t, buf));
       }
       // ---- epilogue of this item: O(t) row / row sum -> out
-      mbar_wait(b_odone(t), (uint32_t)(i & 1));
+      mbar_wait(b_pvdone(t, (c - 1) & 1), (uint32_t)(((c - 1) >> 1) & 1));
       tc_fence_after();
       uint32_t o[32];
       tc_ld32(tO, o);
@@ -460,8 +391,12 @@ __global__ void __launch_bounds__(a8_threads(NQ), NQ == 4 ? 1 : 2) attn8_kernel(
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(b_ofree(t));            // O is in registers: the next item may overwrite it
+      const int item = bid + i * nblk;
+      const int e = (item % nqi) * QROWS + t * 128 + row;
       if (e < S) {
-        const long long tq = seq_token(sm, s, e);
+        const long long sh = item / nqi;
+        const int h = (int)(sh % kH);
+        const long long tq = seq_token(sm, sh / kH, e);
         const float inv = 1.0f / __uint_as_float(o[24]);
 #pragma unroll
         for (int k = 0; k < 6; ++k)
@@ -470,13 +405,7 @@ __global__ void __launch_bounds__(a8_threads(NQ), NQ == 4 ? 1 : 2) attn8_kernel(
                                      __uint_as_float(o[4 * k + 2]) * inv, __uint_as_float(o[4 * k + 3]) * inv),
                          p.round_out);
       }
-      A8_TICK(5);
     }
-    if (dbg && lane == 0) {
-#pragma unroll
-      for (int k = 0; k < 6; ++k) dbg[((size_t)bid * NSW + warp) * 6 + k] = (unsigned long long)tph[k];
-    }
-#undef A8_TICK
   }
   tc_fence_before();
   __syncthreads();
@@ -489,12 +418,12 @@ inline size_t attn8_scratch_bytes(const SeqMap& sm) {
   return (size_t)sm.num_seq * kH * ((size_t)a8_nkt(sm.S) * A8_IMG + (size_t)a8_nqt_pad(sm.S) * A8_QT_BYTES);
 }
 
-template <int NQ, bool USE_TURN, bool SPIN>
-inline int attn8_launch_t(const AttnParams& p, const uint8_t* scratch, cudaStream_t s, std::string* err, bool prof) {
+template <int NQ>
+inline int attn8_launch_t(const AttnParams& p, const uint8_t* scratch, cudaStream_t s, std::string* err) {
   static bool configured[kMaxDevices] = {false};
   const int dev = current_device();
   if (!configured[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(attn8_kernel<NQ, USE_TURN, SPIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, a8_smem_bytes(NQ));
+    cudaError_t e = cudaFuncSetAttribute(attn8_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, a8_smem_bytes(NQ));
     if (e != cudaSuccess) {
       if (err) *err = std::string("cudaFuncSetAttribute(attn8): ") + cudaGetErrorString(e);
       return -2;
@@ -506,49 +435,11 @@ inline int attn8_launch_t(const AttnParams& p, const uint8_t* scratch, cudaStrea
   if (items > 0x7fffffffLL) { if (err) *err = "attn8: too many work items"; return -2; }
   const int per_sm = NQ == 4 ? 1 : 2;
   const int grid = (int)std::min<long long>(items, (long long)per_sm * device_sm_count());
-  unsigned long long* dbg = nullptr;
-  if (prof) {   // debugging aid (attn_variant bit 1): per-warp phase timers, printed after the launch (synchronises!)
-    cudaMalloc(&dbg, ((size_t)grid * 5 * NQ * 6 + 512) * sizeof(unsigned long long));
-    cudaMemsetAsync(dbg, 0, ((size_t)grid * 5 * NQ * 6 + 512) * sizeof(unsigned long long), s);
-  }
-  attn8_kernel<NQ, USE_TURN, SPIN><<<grid, a8_threads(NQ), a8_smem_bytes(NQ), s>>>(p, scratch, (int)items, nqi, dbg);
-  if (prof) {
-    std::vector<unsigned long long> hbuf((size_t)grid * 5 * NQ * 6 + 512);
-    cudaStreamSynchronize(s);
-    cudaMemcpy(hbuf.data(), dbg, hbuf.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
-    cudaFree(dbg);
-    static int printed = 0;
-    if (printed++ < 2) {
-      const char* nm[6] = {"wait s_full", "TMEM load", "max+exp+pack", "wait p_free", "store P", "epilogue"};
-      double tot[6] = {0, 0, 0, 0, 0, 0};
-      for (size_t w = 0; w < (size_t)grid * 4 * NQ; ++w)
-        for (int k = 0; k < 6; ++k) tot[k] += (double)hbuf[w * 6 + k];
-      double all = 0;
-      for (int k = 0; k < 6; ++k) all += tot[k];
-      fprintf(stderr, "attn8 phase timers (mean cycles per softmax warp, %d CTAs, S=%d):", grid, p.sm.S);
-      for (int k = 0; k < 6; ++k) fprintf(stderr, "  %s %.0f (%.1f%%)", nm[k], tot[k] / (grid * 4.0 * NQ), 100.0 * tot[k] / all);
-      fprintf(stderr, "\n");
-      const char* mn[6] = {"wait q_full", "wait kv_full", "wait s_read", "issue QK", "wait p_ready", "o_free + issue PV"};
-      double mt[6] = {0, 0, 0, 0, 0, 0};
-      for (size_t w = 0; w < (size_t)grid * NQ; ++w)
-        for (int k = 0; k < 6; ++k) mt[k] += (double)hbuf[((size_t)grid * 4 * NQ + w) * 6 + k];
-      const unsigned long long* tr = hbuf.data() + (size_t)grid * 5 * NQ * 6;
-      fprintf(stderr, "trace CTA 0 tile 0 (cycles since s_full(20)): tile | s_full seen, s_read arrive, exps done, p_ready arrive | issuer: s_read seen, QK(c+1) issued, p_ready seen, PV issued\n");
-      for (int c = 20; c < 30; ++c) {
-        fprintf(stderr, "  %2d |", c);
-        for (int k = 0; k < 8; ++k) fprintf(stderr, " %6lld%s", (long long)(tr[c * 8 + k] - tr[20 * 8]), k == 3 ? " |" : "");
-        fprintf(stderr, "\n");
-      }
-      fprintf(stderr, "attn8 MMA issuer timers (mean cycles):");
-      for (int k = 0; k < 6; ++k) fprintf(stderr, "  %s %.0f", mn[k], mt[k] / (grid * 1.0 * NQ));
-      fprintf(stderr, "\n");
-    }
-  }
+  attn8_kernel<NQ><<<grid, a8_threads(NQ), a8_smem_bytes(NQ), s>>>(p, scratch, (int)items, nqi);
   return 0;
 }
 
-// flags: bit 0 = force the 2-query-tile kernel (testing), bit 1 = print per-phase timers of the softmax warps (debug),
-//        bit 2 = MUFU turn tokens (A/B experiment), bit 3 = spinning test_wait instead of try_wait (A/B experiment)
+// flags: bit 0 = force the 2-query-tile kernel (testing)
 inline int attn8_launch(const AttnParams& p, uint8_t* scratch, int flags, cudaStream_t s, std::string* err) {
   static bool configured[kMaxDevices] = {false};
   const int dev = current_device();
@@ -560,16 +451,9 @@ inline int attn8_launch(const AttnParams& p, uint8_t* scratch, int flags, cudaSt
     }
     configured[dev] = true;
   }
-  const int nkt = (p.sm.S + 1 + A8_KT - 1) / A8_KT;
-  attn8_prep_kernel<<<(unsigned)(p.sm.num_seq * nkt * 2), 256, A8P_SMEM, s>>>(p, scratch);
+  attn8_prep_kernel<<<(unsigned)(p.sm.num_seq * a8_nkt(p.sm.S) * 2), A8P_THREADS, A8P_SMEM, s>>>(p, scratch);
   const bool small = p.sm.S <= 256 || (flags & 1);
-  const bool prof = (flags & 2) != 0;
-  const bool turn = (flags & 4) != 0, spin = (flags & 8) != 0;
-  int rc;
-  if (small) rc = attn8_launch_t<2, false, false>(p, scratch, s, err, prof);
-  else if (turn) rc = attn8_launch_t<4, true, false>(p, scratch, s, err, prof);
-  else if (spin) rc = attn8_launch_t<4, false, true>(p, scratch, s, err, prof);
-  else rc = attn8_launch_t<4, false, false>(p, scratch, s, err, prof);
+  int rc = small ? attn8_launch_t<2>(p, scratch, s, err) : attn8_launch_t<4>(p, scratch, s, err);
   if (rc) return rc;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {

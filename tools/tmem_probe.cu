@@ -313,6 +313,74 @@ __global__ void __launch_bounds__(128) acc_layout_kernel(int c_format, uint32_t*
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(64u) : "memory");
 }
 
+
+// ---------------------------------------------------------------- part 6
+// Which TMEM columns does one kind::f16 MMA (M = 128, fp32 accumulators) with N = 48 write when its D address is
+// column `col0`? 128 columns are pre-filled with a sentinel.
+__global__ void __launch_bounds__(128) mma_extent_kernel(int N, int col0, uint32_t* out /*[128][128]*/) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t sbase = (raw + 1023u) & ~1023u;
+  uint8_t* sgen = smem_raw + (sbase - raw);
+  uint8_t* As = sgen;                 // 128 rows x 128-byte pitch, SWIZZLE_128B
+  uint8_t* Bs = sgen + 16384;         // up to 64 rows
+  const uint32_t bar = sbase + 16384 + 8192;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sgen + 16384 + 8192 + 16);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (16384 + 8192) / 4; i += 128) reinterpret_cast<uint32_t*>(sgen)[i] = 0;
+  __syncthreads();
+  {
+    const int r = tid;
+    for (int k = 0; k < 16; ++k)
+      reinterpret_cast<uint16_t*>(As + sw128_off(r, k >> 3))[k & 7] = f2h(k == (r & 15) ? 1.f : 0.f);
+    if (r < 64)
+      for (int k = 0; k < 16; ++k)
+        reinterpret_cast<uint16_t*>(Bs + sw128_off(r, k >> 3))[k & 7] = f2h((float)(r + 1 + 100 * k));
+    fence_async_smem();
+  }
+  if (tid == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32((const void*)tmem_slot)), "r"(128u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  {
+    uint32_t z[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) z[i] = 0xDEAD0000u;
+    for (int c = 0; c < 128; c += 32) tc_st32(tmem + ((uint32_t)(warp * 32) << 16) + c, z);
+    tc_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (tid == 0) {
+    const uint32_t idesc = idesc_f16(128, N, 1);
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem + col0), "l"(umma_desc_k128(sbase)), "l"(umma_desc_k128(sbase + 16384)), "r"(idesc), "r"(0u)
+        : "memory");
+    tc_commit(bar);
+  }
+  mbar_wait(bar, 0);
+  tc_fence_after();
+  for (int c = 0; c < 128; c += 32) {
+    uint32_t v[32];
+    tc_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c, v);
+    tc_ld_wait();
+    for (int i = 0; i < 32; ++i) out[tid * 128 + c + i] = v[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128u) : "memory");
+}
+
 static float h2f(uint16_t h) {
   const uint32_t s = (h >> 15) & 1, e = (h >> 10) & 31, m = h & 1023;
   if (e == 0) return (s ? -1.f : 1.f) * (float)m * 5.9604645e-8f;
@@ -366,6 +434,23 @@ int main() {
   if (run_ex2<0>(num_sms, d_cycles, d_sink)) return 1;
   if (run_ex2<1>(num_sms, d_cycles, d_sink)) return 1;
   if (run_ex2<2>(num_sms, d_cycles, d_sink)) return 1;
+  printf("part 6: TMEM columns written by one M=128 kind::f16 MMA\n");
+  CK(cudaFuncSetAttribute(mma_extent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768));
+  {
+    uint32_t* d_o;
+    CK(cudaMalloc(&d_o, 128 * 128 * 4));
+    const int cfgs[][2] = {{48, 0}, {48, 16}, {48, 48}, {32, 96}, {64, 64}, {96, 16}};
+    for (auto& cf : cfgs) {
+      mma_extent_kernel<<<1, 128, 32768>>>(cf[0], cf[1], d_o);
+      CK(cudaDeviceSynchronize());
+      std::vector<uint32_t> o(128 * 128);
+      CK(cudaMemcpy(o.data(), d_o, o.size() * 4, cudaMemcpyDeviceToHost));
+      int lo = 128, hi = -1, ok = 1;
+      for (int c = 0; c < 128; ++c) if (o[1 * 128 + c] != 0xDEAD0000u) { lo = c < lo ? c : lo; hi = c > hi ? c : hi; }
+      for (int n = 0; n < cf[0]; ++n) { float f; memcpy(&f, &o[1 * 128 + cf[1] + n], 4); if (f != (float)(n + 1 + 100)) ok = 0; }
+      printf("  N = %2d at column %3d: row 1 columns [%d, %d] changed, values %s\n", cf[0], cf[1], lo, hi, ok ? "correct" : "WRONG");
+    }
+  }
   printf("part 5: XU pipe cost of the probability pack\n");
   if (run_xu_mix<0>(num_sms, d_cycles, d_sink)) return 1;
   if (run_xu_mix<1>(num_sms, d_cycles, d_sink)) return 1;
