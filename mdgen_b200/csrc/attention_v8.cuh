@@ -45,7 +45,10 @@ constexpr int A8_STAGES = 8;
 constexpr int A8_QT_BYTES = 128 * 64;            // one staged query tile (128 rows x 64 B)
 constexpr float A8_MASKED = -30000.0f;           // score offset of a masked key (exp2 -> exactly 0)
 constexpr int A8_TSTRIDE = 128, A8_S1 = A8_KT, A8_OCOL = 96;   // TMEM columns: per query tile, S buffer 1, O
-constexpr float A8_LAZY = 8.0f;                  // the softmax reference moves only when the row maximum grows by > 2^8
+constexpr float A8_LAZY = 8.0f;
+#ifndef A8_POLY_EVERY
+#define A8_POLY_EVERY 3                           // one score pair in 3 is exponentiated on the FMA pipe (measured best of 2, 3, 4)
+#endif                  // the softmax reference moves only when the row maximum grows by > 2^8
 
 __host__ __device__ constexpr int a8_threads(int nq) { return (5 * nq + 1) * 32; }
 __host__ __device__ constexpr int a8_smem_bytes(int nq) {
@@ -68,6 +71,36 @@ __device__ __forceinline__ uint64_t umma_desc_k64(uint32_t smem_addr) {
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)4 << 61;
   return d;
+}
+
+// 2^x for two scores on the FMA pipe instead of the MUFU pipe (which bounds this kernel: ncu XU pipe 77 %), packed to
+// an fp16 pair. Cody-Waite split with the 1.5 * 2^23 magic number (t = x + magic holds round(x) in its low mantissa
+// bits), degree-3 minimax polynomial for 2^f on [-0.5, 0.5] (max relative error 7.5e-5, below fp16's half ulp of
+// 2.4e-4), exponent re-inserted with an integer shift-add. The three adds and three FMAs are Blackwell's packed
+// fp32x2 instructions (add.f32x2 / fma.f32x2: one issue slot for both values). Valid for x <= 127; x is clamped at
+// -125 (a masked key's -30000 becomes 2^-125, which rounds to 0 in fp16).
+__device__ __forceinline__ uint32_t exp2_poly_pack_f16x2(float x0, float x1) {
+  constexpr uint64_t kMagic = 0x4B4000004B400000ull;      // {12582912.f, 12582912.f}
+  constexpr uint64_t kNegMagic = 0xCB400000CB400000ull;
+  constexpr uint64_t kNegOne = 0xBF800000BF800000ull;
+  constexpr uint64_t kC0 = 0x3F7FFB493F7FFB49ull;         // 0.99992806
+  constexpr uint64_t kC1 = 0x3F31798D3F31798Dull;         // 0.69326097
+  constexpr uint64_t kC2 = 0x3E786F0D3E786F0Dull;         // 0.24261113
+  constexpr uint64_t kC3 = 0x3D61FBB03D61FBB0ull;         // 0.05517167
+  x0 = fmaxf(x0, -125.0f);
+  x1 = fmaxf(x1, -125.0f);
+  uint64_t X, T, N, F, P;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(X) : "f"(x0), "f"(x1));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(T) : "l"(X), "l"(kMagic));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(N) : "l"(T), "l"(kNegMagic));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(F) : "l"(N), "l"(kNegOne), "l"(X));      // f = x - round(x)
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(P) : "l"(F), "l"(kC3), "l"(kC2));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(P) : "l"(P), "l"(F), "l"(kC1));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(P) : "l"(P), "l"(F), "l"(kC0));
+  uint32_t p0, p1, t0, t1;
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(p0), "=r"(p1) : "l"(P));
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(t0), "=r"(t1) : "l"(T));
+  return pack_f16x2_rn(__uint_as_float(p0 + (t0 << 23)), __uint_as_float(p1 + (t1 << 23)));
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -183,7 +216,7 @@ __global__ void __launch_bounds__(A8P_THREADS, 2) attn8_prep_kernel(AttnParams p
 // P over buffer b) -> P·V -> pv_done[t][b] (O includes that tile);
 // o_free[t] once per item (epilogue has read O). Shared: kv_full / kv_free per ring stage (kv_free counts the NQ
 // issuers), q_full / q_free per query double buffer.
-template <int NQ>
+template <int NQ, bool POLY>
 __global__ void __launch_bounds__(a8_threads(NQ), NQ == 4 ? 1 : 2) attn8_kernel(AttnParams p, const uint8_t* __restrict__ scratch,
                                                                             int total_items, int nqi /*items per (seq, head)*/) {
   constexpr int NSW = 4 * NQ;                    // softmax warps
@@ -362,12 +395,19 @@ __global__ void __launch_bounds__(a8_threads(NQ), NQ == 4 ? 1 : 2) attn8_kernel(
         }
         m_ref = m_new;
         // ---- P = exp2(S - m_ref) as fp16 pairs (in the score registers), stored over the first 24 score columns
+        // (every A8_POLY_EVERY-th pair is exponentiated on the FMA pipe, the others on the MUFU pipe)
 #pragma unroll
-        for (int k = 0; k < 16; ++k)
-          va[k] = pack_f16x2_rn(ex2f(__uint_as_float(va[2 * k]) - m_new), ex2f(__uint_as_float(va[2 * k + 1]) - m_new));
+        for (int k = 0; k < 16; ++k) {
+          const float x0 = __uint_as_float(va[2 * k]) - m_new, x1 = __uint_as_float(va[2 * k + 1]) - m_new;
+          va[k] = (POLY && (k % A8_POLY_EVERY) == A8_POLY_EVERY - 1) ? exp2_poly_pack_f16x2(x0, x1)
+                                                                      : pack_f16x2_rn(ex2f(x0), ex2f(x1));
+        }
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          vb[k] = pack_f16x2_rn(ex2f(__uint_as_float(vb[2 * k]) - m_new), ex2f(__uint_as_float(vb[2 * k + 1]) - m_new));
+        for (int k = 0; k < 8; ++k) {
+          const float x0 = __uint_as_float(vb[2 * k]) - m_new, x1 = __uint_as_float(vb[2 * k + 1]) - m_new;
+          vb[k] = (POLY && (k % A8_POLY_EVERY) == A8_POLY_EVERY - 1) ? exp2_poly_pack_f16x2(x0, x1)
+                                                                      : pack_f16x2_rn(ex2f(x0), ex2f(x1));
+        }
         {
           uint32_t p0[16], p1[8];
 #pragma unroll
@@ -418,12 +458,12 @@ inline size_t attn8_scratch_bytes(const SeqMap& sm) {
   return (size_t)sm.num_seq * kH * ((size_t)a8_nkt(sm.S) * A8_IMG + (size_t)a8_nqt_pad(sm.S) * A8_QT_BYTES);
 }
 
-template <int NQ>
+template <int NQ, bool POLY>
 inline int attn8_launch_t(const AttnParams& p, const uint8_t* scratch, cudaStream_t s, std::string* err) {
   static bool configured[kMaxDevices] = {false};
   const int dev = current_device();
   if (!configured[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(attn8_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, a8_smem_bytes(NQ));
+    cudaError_t e = cudaFuncSetAttribute(attn8_kernel<NQ, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, a8_smem_bytes(NQ));
     if (e != cudaSuccess) {
       if (err) *err = std::string("cudaFuncSetAttribute(attn8): ") + cudaGetErrorString(e);
       return -2;
@@ -435,11 +475,12 @@ inline int attn8_launch_t(const AttnParams& p, const uint8_t* scratch, cudaStrea
   if (items > 0x7fffffffLL) { if (err) *err = "attn8: too many work items"; return -2; }
   const int per_sm = NQ == 4 ? 1 : 2;
   const int grid = (int)std::min<long long>(items, (long long)per_sm * device_sm_count());
-  attn8_kernel<NQ><<<grid, a8_threads(NQ), a8_smem_bytes(NQ), s>>>(p, scratch, (int)items, nqi);
+  attn8_kernel<NQ, POLY><<<grid, a8_threads(NQ), a8_smem_bytes(NQ), s>>>(p, scratch, (int)items, nqi);
   return 0;
 }
 
-// flags: bit 0 = force the 2-query-tile kernel (testing)
+// flags: bit 0 = force the 2-query-tile kernel (testing), bit 1 = all exponentials on the MUFU pipe (A/B of the
+//        FMA-pipe polynomial that otherwise takes every A8_POLY_EVERY-th score pair)
 inline int attn8_launch(const AttnParams& p, uint8_t* scratch, int flags, cudaStream_t s, std::string* err) {
   static bool configured[kMaxDevices] = {false};
   const int dev = current_device();
@@ -453,7 +494,9 @@ inline int attn8_launch(const AttnParams& p, uint8_t* scratch, int flags, cudaSt
   }
   attn8_prep_kernel<<<(unsigned)(p.sm.num_seq * a8_nkt(p.sm.S) * 2), A8P_THREADS, A8P_SMEM, s>>>(p, scratch);
   const bool small = p.sm.S <= 256 || (flags & 1);
-  int rc = small ? attn8_launch_t<2>(p, scratch, s, err) : attn8_launch_t<4>(p, scratch, s, err);
+  const bool poly = (flags & 2) == 0;
+  int rc = small ? (poly ? attn8_launch_t<2, true>(p, scratch, s, err) : attn8_launch_t<2, false>(p, scratch, s, err))
+                 : (poly ? attn8_launch_t<4, true>(p, scratch, s, err) : attn8_launch_t<4, false>(p, scratch, s, err));
   if (rc) return rc;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
