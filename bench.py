@@ -12,6 +12,11 @@ sampling call (mdgen/transport/integrators.py:90-113) over B trajectories of T f
   e2e   : same metric through the public API NewMDGenWrapper.inference(batch) with HOST (pinned)
           buffers: H2D of the batch, featurisation, noise, sampling, decode to atom14, D2H.
 Batches shard across ranks with no data-path collective: "scaling": "weak".
+
+`--impl reference` runs the UNMODIFIED reference (oracle/_ref, the sha256-pinned copy of /root/reference/mdgen made by
+oracle/vendor_reference.py) through its own sampler API on the SAME GPU in strict fp32 - the denominator of the
+north-star's ">= 10x the reference single-GPU PyTorch" - on a bounded sample (16 of the 64 trajectories per step, all 100
+Euler steps: measured time, nothing extrapolated), and reports the reference's CPU path beside it (`cpu_baseline`).
 """
 import argparse
 import json
@@ -27,6 +32,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "sampled frames/sec (1000x4-token seq, 100 Euler steps)"
 C, H, FF = 384, 16, 1536
+REF_BATCH = 16     # trajectories per step of the reference arm (bounded sample of the 64-trajectory workload)
 
 
 def flops_forward(N, T, L, layers=5):
@@ -46,7 +52,8 @@ def parse_args():
     p.add_argument("--euler-steps", type=int, default=100)
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu-baseline", action="store_true")
-    p.add_argument("--no-torch-gpu", action="store_true", help="skip timing the stock-ATen port on the GPU")
+    p.add_argument("--no-torch-gpu", action="store_true", help="skip timing the reference on the GPU")
+    p.add_argument("--no-extra", action="store_true", help="skip the extra configurations (ATLAS-shaped, upsampling, strong scaling)")
     p.add_argument("--use-tc", type=int, default=-1, help="-1 = library default")
     p.add_argument("--use-graph", type=int, default=-1, help="-1 = library default (CUDA-graph step replay for small workloads)")
     return p.parse_args()
@@ -61,6 +68,13 @@ def load_peaks():
                 "source": "measured"}
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0,
             "source": "fallback"}
+
+
+def load_profile_facts():
+    """ncu-derived facts of the dominant kernel (DRAM bytes per launch, limiter), committed under profiles/ by
+    tools/ncu_summary.py from the raw export of the same build; bench.py never hard-codes them."""
+    path = os.path.join(ROOT, "profiles", "roofline_facts.json")
+    return json.load(open(path)) if os.path.isfile(path) else {}
 
 
 class ClockSampler:
@@ -107,92 +121,149 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_port_run(B, T, L, k_sample, euler_steps, threads):
-    """Times the oracle port (CPU restatement of the reference path) on a bounded sample:
-    `k_sample` of the `euler_steps` Euler steps for B trajectories; returns extrapolated frames/s."""
-    import torch
-    from mdgen_b200.config import config_from_args, default_args
-    from mdgen_b200.synthetic import (euler_time_grid, synthetic_batch, synthetic_noise,
-                                      synthetic_state_dict)
-    from oracle import mdgen_oracle as O
-    torch.set_num_threads(threads)
-    args = default_args(sim_condition=True, prepend_ipa=True, abs_pos_emb=(L == 4), crop=L, num_frames=T)
-    cfg = config_from_args(args)
-    sd = synthetic_state_dict(cfg, seed=0)
-    batch = synthetic_batch(B, T, L, seed=1, vary_frames=False)
-    zs = synthetic_noise(B, T, L, cfg.latent_dim, seed=2)
-    grid = euler_time_grid(euler_steps)[: k_sample + 1]
-    with torch.no_grad():
-        t0 = time.perf_counter()
-        op = O.prep_batch(cfg, batch)
-        kw = dict(mask=op["mask"], start=op["start"], end=op["end"], x_cond=op["x_cond"],
-                  x_cond_mask=op["x_cond_mask"], aatype=op["aatype"])
-        t1 = time.perf_counter()
-        O.sample_euler(sd, cfg, zs, grid, **kw)
-        t2 = time.perf_counter()
-    per_step = (t2 - t1) / k_sample
-    full = per_step * euler_steps
-    return B * T / full, {"prep_s": t1 - t0, "sec_per_euler_step": per_step}
+# reference legs (the only places that touch oracle/)
+def _bench_args_kw(T, L, **extra):
+    kw = dict(sim_condition=True, prepend_ipa=True, abs_pos_emb=(L == 4), crop=L, num_frames=T,
+              sampling_method="euler")
+    kw.update(extra)
+    return kw
 
 
-def best_cpu_threads(T, L):
-    """torch CPU ops on this path stop scaling (and regress) well before 128 threads: pick the
-    thread count that maximises the port's forward throughput on this host."""
-    import torch
-    from mdgen_b200.config import config_from_args, default_args
-    from mdgen_b200.synthetic import synthetic_batch, synthetic_noise, synthetic_state_dict
-    from oracle import mdgen_oracle as O
-    ncpu = os.cpu_count() or 1
-    cands = sorted({c for c in (8, 16, 32, 64, ncpu) if c <= ncpu})
-    args = default_args(sim_condition=True, prepend_ipa=True, abs_pos_emb=(L == 4), crop=L, num_frames=T)
-    cfg = config_from_args(args)
-    sd = synthetic_state_dict(cfg, seed=0)
-    batch = synthetic_batch(1, T, L, seed=1, vary_frames=False)
-    zs = synthetic_noise(1, T, L, cfg.latent_dim, seed=2)
-    op = O.prep_batch(cfg, batch)
-    kw = dict(mask=op["mask"], start=op["start"], end=op["end"], x_cond=op["x_cond"],
-              x_cond_mask=op["x_cond_mask"], aatype=op["aatype"])
-    best, best_t = cands[0], float("inf")
-    for c in cands:
-        torch.set_num_threads(c)
+class RefModel:
+    """The reference's own NewMDGenWrapper (oracle/_ref) or, when that copy is absent, the oracle port; strict fp32."""
+
+    def __init__(self, T, L, device, stress=False):
+        import torch
+        from mdgen_b200.config import config_from_args, default_args
+        from mdgen_b200.synthetic import synthetic_state_dict
+        from oracle import ref_loader
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
+        self.device = device
+        self.cfg = config_from_args(default_args(**_bench_args_kw(T, L)))
+        sd = synthetic_state_dict(self.cfg, seed=0, stress=stress)
+        self.kind = "reference" if ref_loader.reference_available() else "port"
+        if self.kind == "reference":
+            self.source = ref_loader.reference_kind()
+            self.m = ref_loader.reference_wrapper(ref_loader.make_args(**_bench_args_kw(T, L)), sd, device)
+            self.eigh = ref_loader.chunked_eigh_patch
+        else:
+            from oracle import mdgen_oracle as O
+            self.O = O
+            self.sd = {k: v.to(device) for k, v in sd.items()}
+
+    def prep(self, batch):
+        """batch on self.device -> opaque conditioning (the reference's own prep_batch)."""
+        import torch
         with torch.no_grad():
-            O.forward(sd, cfg, zs, torch.zeros(1), **kw)   # warm
-            t0 = time.perf_counter()
-            O.forward(sd, cfg, zs, torch.zeros(1), **kw)
-            dt = time.perf_counter() - t0
+            if self.kind == "reference":
+                with self.eigh():
+                    return self.m.prep_batch(batch)["model_kwargs"]
+            op = self.O.prep_batch(self.cfg, batch)
+            return dict(mask=op["mask"], start=op["start"], end=op["end"], x_cond=op["x_cond"],
+                        x_cond_mask=op["x_cond_mask"], aatype=op["aatype"])
+
+    def forward(self, x, t, kw):
+        import torch
+        with torch.no_grad():
+            if self.kind == "reference":
+                return self.m.model.forward_inference(x, t, **kw)
+            return self.O.forward(self.sd, self.cfg, x, t, **kw)
+
+    def sample(self, zs, K, kw, k_run=None):
+        """Fixed-grid Euler through the reference's sampler API; k_run < K integrates only the first k_run steps."""
+        import torch
+        from functools import partial
+        from mdgen_b200.synthetic import euler_time_grid
+        with torch.no_grad():
+            if self.kind == "reference" and (k_run is None or k_run == K):
+                fn = self.m.transport_sampler.sample_ode(sampling_method="euler", num_steps=K + 1)
+                return fn(zs, partial(self.m.model.forward_inference, **kw))[-1]
+            grid = euler_time_grid(K)[: (k_run or K) + 1].to(zs.device)
+            if self.kind == "reference":     # same Euler recurrence the torchdiffeq stand-in runs, on a grid prefix
+                f = partial(self.m.model.forward_inference, **kw)
+                x = zs
+                for i in range(len(grid) - 1):
+                    x = x + (grid[i + 1] - grid[i]) * f(x, grid[i] * torch.ones(x.shape[0], device=x.device))
+                return x
+            return self.O.sample_euler(self.sd, self.cfg, zs, grid, **kw)
+
+
+def cpu_reference_sample(T, L, K, k_sample=2):
+    """The reference's CPU path on a bounded sample: 1 trajectory, k_sample of the K Euler steps, all host threads
+    that help (torch CPU ops on this path stop scaling well before 128 threads). Returns (frames/s, cores, text)."""
+    import torch
+    from mdgen_b200.synthetic import synthetic_batch, synthetic_noise
+    ncpu = os.cpu_count() or 1
+    ref = RefModel(T, L, "cpu")
+    batch = synthetic_batch(1, T, L, seed=1, vary_frames=False)
+    zs = synthetic_noise(1, T, L, ref.cfg.latent_dim, seed=2)
+    kw = ref.prep(batch)
+    best, best_t = None, float("inf")
+    for c in sorted({c for c in (8, 16, 32, 64, ncpu) if c <= ncpu}):
+        torch.set_num_threads(c)
+        ref.forward(zs, torch.zeros(1), kw)
+        t0 = time.perf_counter()
+        ref.forward(zs, torch.zeros(1), kw)
+        dt = time.perf_counter() - t0
         if dt < best_t:
             best, best_t = c, dt
-    return best
+    torch.set_num_threads(best)
+    t0 = time.perf_counter()
+    ref.sample(zs, K, kw, k_run=k_sample)
+    per_step = (time.perf_counter() - t0) / k_sample
+    text = (f"{'unmodified reference (oracle/_ref)' if ref.kind == 'reference' else 'oracle port'} on the host CPU: "
+            f"B=1 x T={T} x L={L}, {k_sample} of {K} Euler steps timed ({per_step:.2f} s/step, best of "
+            f"8/16/32/64/all threads), scaled to {K} steps")
+    return T / (per_step * K), best, ref.kind, text
 
 
 def run_reference(a, rank, world):
-    """--impl reference: the reference's CPU implementation of the path. The reference is Python
-    and cannot travel to the GPU box, so this is the pinned oracle port (oracle/mdgen_oracle.py),
-    all host threads, each step a bounded sample of the workload."""
+    """--impl reference (rank 0 only): the unmodified reference on this GPU, bounded sample per step."""
     if rank != 0:
         return
-    threads = best_cpu_threads(a.frames, a.residues)
-    kb, ks = 1, 2   # 1 trajectory, 2 of the 100 Euler steps per bench step (~3-4 s of CPU work)
-    vals = []
-    for i in range(a.warmup + a.steps):
-        v, _ = cpu_port_run(kb, a.frames, a.residues, ks, a.euler_steps, threads)
-        if i >= a.warmup:
-            vals.append(v)
-    value = statistics.mean(vals)
-    sample = (f"oracle port, B={kb} trajectory x T={a.frames} x L={a.residues}, {ks} of {a.euler_steps} "
-              f"Euler steps timed, extrapolated x{a.euler_steps // ks}")
-    line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": a.gpus,
-        "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * kb * a.frames / value,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic",
-        "config": {"workload": f"tetrapeptide forward-sim T={a.frames} L={a.residues} "
-                               f"{a.euler_steps} Euler steps (CPU sample)", "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "kind": "port",
-                         "sample": sample},
-        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-    }
+    import torch
+    from mdgen_b200.synthetic import synthetic_batch, synthetic_noise
+    T, L, K = a.frames, a.residues, a.euler_steps
+    line = {"impl": "reference", "metric": METRIC, "unit": "frames/s", "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "gpu_launches": 0}
+    cpu_v, cores, kind, cpu_text = cpu_reference_sample(T, L, K)
+    line["cpu_baseline"] = {"value": cpu_v, "unit": "frames/s", "cores": cores, "kind": kind, "sample": cpu_text}
+    if torch.cuda.is_available():
+        dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+        torch.cuda.set_device(dev)
+        ref = RefModel(T, L, dev)
+        Bs = min(REF_BATCH, a.batch)
+        batch = {k: v.to(dev) for k, v in synthetic_batch(Bs, T, L, seed=1, vary_frames=False).items()}
+        zs = synthetic_noise(Bs, T, L, ref.cfg.latent_dim, seed=2).to(dev)
+        kw = ref.prep(batch)
+        clocks = ClockSampler(dev.index or 0)
+        for _ in range(a.warmup):
+            ref.sample(zs, K, kw)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(a.steps):
+            ref.sample(zs, K, kw)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / a.steps
+        value = Bs * T / (ms / 1e3)
+        sample = (f"{'unmodified reference (oracle/_ref: ' + ref.source + ')' if ref.kind == 'reference' else 'oracle port'}"
+                  f" on cuda:{dev.index or 0}, strict fp32 (allow_tf32 off): {Bs} of the {a.batch} trajectories per step, "
+                  f"all {K} Euler steps through its own sample_ode('euler') - measured, not extrapolated")
+        line.update({"value": value, "ms_per_step": ms, "clocks": clocks.stop(),
+                     "config": {"workload": f"tetrapeptide forward-sim num_frames={T} crop={L}, {K} Euler steps "
+                                            f"(BASELINE.json configs[1])", "sample": sample, "device": "cuda",
+                                "reference_kind": ref.kind},
+                     "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    else:   # no GPU: the CPU sample is all there is
+        line.update({"value": cpu_v, "ms_per_step": 1e3 * T / cpu_v,
+                     "config": {"workload": f"tetrapeptide forward-sim num_frames={T} crop={L}, {K} Euler steps "
+                                            f"(BASELINE.json configs[1])", "sample": cpu_text, "device": "cpu",
+                                "reference_kind": kind},
+                     "e2e": {"value": cpu_v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
     print(json.dumps(line), flush=True)
 
 
@@ -209,7 +280,7 @@ def main():
     import torch
     import torch.distributed as dist
     from mdgen_b200.config import default_args
-    from mdgen_b200.dist import gather_counts, max_over_ranks, rank_seed
+    from mdgen_b200.dist import gather_counts, max_over_ranks, rank_seed, shard_range
     from mdgen_b200.synthetic import (euler_time_grid, synthetic_batch, synthetic_noise,
                                       synthetic_state_dict)
     from mdgen_b200.wrapper import NewMDGenWrapper
@@ -222,11 +293,13 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     B, T, L, K = a.batch, a.frames, a.residues, a.euler_steps
-    args = default_args(sim_condition=True, prepend_ipa=True, abs_pos_emb=(L == 4), crop=L,
-                        num_frames=T, sampling_method="euler")
-    m = NewMDGenWrapper(args)
-    m.model.load_state_dict(synthetic_state_dict(m.cfg, seed=0))
-    m = m.eval().to(dev)
+
+    def make_model(T_, L_, **extra):
+        m_ = NewMDGenWrapper(default_args(**_bench_args_kw(T_, L_, **extra)))
+        m_.model.load_state_dict(synthetic_state_dict(m_.cfg, seed=0))
+        return m_.eval().to(dev)
+
+    m = make_model(T, L)
     eng = m.model.engine()
     if a.use_tc >= 0:
         eng.set_option("use_tc", a.use_tc)
@@ -291,13 +364,19 @@ def main():
                "d2h_bytes_per_step": d2h, "ms_per_step": ms_e,
                "api": "NewMDGenWrapper.inference(batch) on pinned host tensors -> atom14.cpu()"}
 
-    # ---- per-kernel device time of one profiled sampling call (CUDA events on the launch stream,
-    #      recorded inside the library around every kernel family)
+    # ---- per-kernel device time of one profiled sampling call + one profiled public-API call (CUDA events on the
+    #      launch stream, recorded inside the library around every kernel family)
     eng.set_option("profile", 1)
     hot()
     prof = eng.profile_dump()
+    db = {k: v.to(dev, non_blocking=True) for k, v in hbatch.items()}
+    atom14, _ = m.inference(db, num_steps=2)                 # prep + decode families (2 Euler steps)
+    eng.featurize_atom14(atom14.reshape(B * T, L, 14, 3), dbatch["seqres"].repeat_interleave(T, 0))
+    prof_api = eng.profile_dump()
     eng.set_option("profile", 0)
+    del atom14
     peaks = load_peaks()
+    facts = load_profile_facts()
     N = B * T * L
     fam_flops = {  # algorithmic FLOPs per launch of each tensor-bound family
         "gemm_qkv": 2 * N * 1152 * C, "gemm_out": 2 * N * C * C, "gemm_fc1": 2 * N * FF * C,
@@ -310,94 +389,121 @@ def main():
     achieved = fam_flops[dom] / (dom_ms / 1e3) / 1e12
     peak = peaks["bf16_tflops_sustained"]
     use_tc = eng.get_option("use_tc")
+    gdt = eng.get_option("gemm_bf16")
     fam_tflops = {k: round(fam_flops[k] / (prof[k][0] / prof[k][1] / 1e3) / 1e12, 1) for k in fam_flops if k in prof}
-    # DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/r1_attention_ncu.md:
-    # attn_tc_kernel<PV16> 1.14 GB read + 0.19 GB write, attn_prep2_kernel 0.40 + 0.60 GB) — valid for this workload only
-    traffic = 2.33e9 if (dom == "mha_t" and (B, T, L) == (64, 1000, 4)) else None
+    # HBM-bound side kernels: algorithmic bytes per token (or residue) per launch / measured time, against the copy peak
+    side_bytes = {"ln_mod": 4 * C + 2 * C, "embed": 4 * D + 4 * C + 4 * C, "final": 4 * C + 2 * 4 * D,
+                  "mha_l": 2 * 3 * C + 2 * C, "prep": 104 + 2 * 4 * D + 8, "decode": 4 * D + 168,
+                  "featurize": 168 + 104 + 28}
+    side = {}
+    for name, bpt in side_bytes.items():
+        src = prof if name in prof else prof_api
+        if name in src and src[name][0] > 0:
+            gbs = bpt * N / (src[name][0] / src[name][1] / 1e3) / 1e9
+            side[name] = {"gbs": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peaks["hbm_gbs"], 3),
+                          "bytes_per_token": bpt, "ms": round(src[name][0] / src[name][1], 4)}
+    fact = facts.get(f"{dom}:{B}x{T}x{L}", {})
     roofline = {
         "kernel": dom, "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-        "frac": achieved / peak, "traffic": traffic, "family_tflops": fam_tflops,
-        "note": "mha_t = attn_prep2_kernel + attn_tc_kernel; at head_dim 24 it is bound by TMEM read bandwidth "
-                "(every fp32 score is read back once: 64 B/clk/SM) and the MUFU ex2 pipe (96 MMA FLOP per "
-                "exponential), not by the tensor pipe - see profiles/r1_attention_ncu.md; the GEMM families' "
-                "achieved TFLOP/s are in family_tflops",
-        "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']}); "
-                       + ("token GEMMs and attention P.V: bf16 operands (kind::f16), attention Q.K^T: TF32 operands"
-                          if use_tc else "fp32 SIMT FMA (validation path), not the tensor pipe"),
+        "frac": achieved / peak, "traffic": fact.get("traffic"), "family_tflops": fam_tflops,
+        "note": "mha_t = attn8_prep_kernel + attn8_kernel (fp16 QK^T and P.V on tcgen05); at head_dim 24 there are only "
+                "96 MMA FLOP per exponential, so its real limiter is the MUFU ex2 pipe (see `limiter`), not the tensor "
+                "pipe; the GEMM families' achieved TFLOP/s are in family_tflops",
+        "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']}); fp16 operands run at the bf16 rate",
         "avg_launch_ms": dom_ms, "launches": prof[dom][1], "time_shares": shares,
-        # the resource that actually limits the dominant kernel, from the committed ncu capture of this workload
-        "limiter": ({"resource": "TMEM read bandwidth (tcgen05.ld of the fp32 score tiles)", "achieved": 44.8,
-                     "peak": 64.0, "unit": "B/clk/SM", "frac": 0.70,
-                     "source": "profiles/r1_attention_ncu.md: 10.2 M LDTM.x16 x 2 KB in the 1.665 ms attn_tc_kernel; "
-                               "peak from the microarchitecture notes (TMEM read 64 B/clk/SM); MUFU pipe 65 %"}
-                    if (dom == "mha_t" and (B, T, L) == (64, 1000, 4)) else None),
+        "limiter": fact.get("limiter"), "facts_source": fact.get("source"),
+        "side_kernels": {"peak_gbs": peaks["hbm_gbs"], "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peaks['source']})",
+                         **side},
         "whole_step_tflops": flops_forward(N, T, L) * K / (ms_per_step / 1e3) / 1e12,
     }
 
-    # ---- the north-star's denominator: the reference's stock-ATen formulation (materialised fp32
-    #      attention, no TF32) on the SAME B200, here through the pinned oracle port (it omits the
-    #      reference's wasted head-mean of the attention weights, mha.py:399-405, so it is if anything
-    #      faster than the real reference). Bounded sample: 2 of the K Euler steps, extrapolated.
+    # ---- extra configurations (SURVEY.md §8d / BASELINE.json configs[2], [4]) and a strong-scaling point, timed after
+    #      the headline with one warm-up and one timed sampling call each (all ranks; max over ranks)
+    extra = None
+    if not a.no_extra:
+        extra = {}
+
+        def run_cfg(name, Bx, Tx, Lx, total_traj_x, note, **model_kw):
+            try:
+                mx = make_model(Tx, Lx, **model_kw)
+                bx = {k: v.to(dev) for k, v in synthetic_batch(Bx, Tx, Lx, seed=rank_seed(11, rank), vary_frames=False,
+                                                               cond_interval=model_kw.get("cond_interval", 0) or 0).items()}
+                zx = synthetic_noise(Bx, Tx, Lx, mx.latent_dim, seed=rank_seed(12, rank)).to(dev)
+                kwx = mx.prep_batch(bx)["model_kwargs"]
+                fn = lambda: mx.model.sample_euler(zx, grid, **kwx)
+                fn()
+                msx = timed(fn, 1)
+                extra[name] = {"value": total_traj_x * Tx / (msx / 1e3), "unit": "frames/s", "ms_per_step": msx,
+                               "config": note, "tflops": flops_forward(Bx * Tx * Lx, Tx, Lx) * K * world / (msx / 1e3) / 1e12}
+                del mx, bx, zx, kwx
+                torch.cuda.empty_cache()
+            except Exception as ex:
+                extra[name] = {"error": repr(ex)[:200]}
+
+        run_cfg("atlas_shaped", 1, 250, 256, world, f"ATLAS forward-sim num_frames=250 crop=256 (64,000 tokens), 1 protein per "
+                f"GPU, {K} Euler steps (BASELINE.json configs[4] shape), weak")
+        run_cfg("upsampling", 16, 1000, 4, 16 * world, f"tetrapeptide upsampling num_frames=1000 cond_interval=100, 16 per GPU, "
+                f"{K} Euler steps (BASELINE.json configs[2] shape), weak", cond_interval=100)
+        s0, s1 = shard_range(64, rank, world)
+        run_cfg("strong_scaling_c2", max(1, s1 - s0), T, L, 64, f"BASELINE.json configs[1] with 64 trajectories TOTAL split over "
+                f"{world} rank(s) ({max(1, s1 - s0)} on this rank): strong scaling")
+
+    # ---- the north-star's denominator measured beside ours: the unmodified reference on the SAME GPU (strict fp32),
+    #      B trajectories, the first 5 of the K Euler steps of its own recurrence timed; and the parity spot check
+    #      on this very batch: forward velocities of the two implementations on identical inputs
     torch_gpu = None
     if rank == 0 and not a.no_torch_gpu:
         try:
-            from oracle import mdgen_oracle as O
-            torch.backends.cuda.matmul.allow_tf32 = False
-            torch.backends.cudnn.allow_tf32 = False
-            sd_dev = {k_: v_.to(dev) for k_, v_ in synthetic_state_dict(m.cfg, seed=0).items()}
-            with torch.no_grad():
-                # featurisation taken from our prep kernel (the reference's batched 4x4 eigh,
-                # rigid_utils.py:191-210, fails in cuSOLVER at 256,000 matrices on this stack)
-                okw = dict(mask=kw["mask"].float(), start=(dbatch["rots"][:, 0], dbatch["trans"][:, 0]),
-                           end=(dbatch["rots"][:, -1], dbatch["trans"][:, -1]), x_cond=kw["x_cond"],
-                           x_cond_mask=kw["x_cond_mask"], aatype=kw["aatype"])
-                ks = 2
-                g2 = grid[: ks + 1]
-                O.sample_euler(sd_dev, m.cfg, zs, grid[:2], **okw)      # warm-up (1 step)
-                torch.cuda.synchronize()
-                t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                t0.record()
-                xr = O.sample_euler(sd_dev, m.cfg, zs, g2, **okw)
-                t1.record()
-                torch.cuda.synchronize()
-                ms_ref = t0.elapsed_time(t1) / ks
-                # same-step agreement of our path with the port on this very input (sanity, not the parity gate)
-                xo = m.model.sample_euler(zs, g2, **kw)
-                agree = float((xo - xr).abs().max() / xr.abs().max())
+            ref = RefModel(T, L, dev)
+            rkw = ref.prep(dbatch)
+            tq = torch.full((B,), 0.3, device=dev)
+            v_ref = ref.forward(zs, tq, rkw)
+            v_our = m.model.forward_inference(zs, tq, **kw)
+            vel_max = float((v_our - v_ref).abs().max() / v_ref.abs().max())
+            vel_l2 = float((v_our - v_ref).norm() / v_ref.norm())
+            del v_ref, v_our
+            ks = 5
+            ref.sample(zs, K, rkw, k_run=1)
+            torch.cuda.synchronize()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            ref.sample(zs, K, rkw, k_run=ks)
+            t1.record()
+            torch.cuda.synchronize()
+            ms_ref = t0.elapsed_time(t1) / ks
             torch_gpu = {"value": B * T / (ms_ref * K / 1e3), "unit": "frames/s", "ms_per_euler_step": ms_ref,
-                         "sample": f"oracle port (stock ATen, fp32, allow_tf32=False) on this B200: B={B}, "
-                                   f"{ks} of {K} Euler steps timed, extrapolated", "max_rel_diff_vs_ours_2_steps": agree}
-            del sd_dev, xr, xo, okw
+                         "kind": ref.kind,
+                         "sample": f"{'unmodified reference (oracle/_ref)' if ref.kind == 'reference' else 'oracle port'} on this "
+                                   f"B200, strict fp32: B={B}, {ks} of {K} Euler steps timed, scaled to {K}",
+                         "velocity_max_rel_diff_vs_ours": vel_max, "velocity_rel_l2_diff_vs_ours": vel_l2,
+                         "velocity_check": f"forward_inference at t=0.3 on the bench batch (B={B}); north-star tolerance 1e-3"}
+            del ref, rkw
             torch.cuda.empty_cache()
         except Exception as e:  # e.g. out of memory for the materialised score tensors
             torch_gpu = {"unavailable": repr(e)[:200]}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        threads = best_cpu_threads(T, L)
-        v, extra = cpu_port_run(1, T, L, 4, K, threads)
-        cpu_baseline = {"value": v, "unit": "frames/s", "cores": threads, "kind": "port",
-                        "sample": f"oracle port: B=1 x T={T} x L={L}, 4 of {K} Euler steps timed "
-                                  f"({extra['sec_per_euler_step']:.2f} s/step, best of 8/16/32/64/all threads), "
-                                  f"extrapolated x{K / 4:g}"}
+        v, cores, kind, text = cpu_reference_sample(T, L, K, k_sample=4)
+        cpu_baseline = {"value": v, "unit": "frames/s", "cores": cores, "kind": kind, "sample": text}
 
     if rank == 0:
+        dtype = {0: "tf32", 1: "bf16", 2: "f16"}.get(gdt, "f16") if use_tc else "f32"
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None,
-            "dtype": ("bf16" if eng.get_option("gemm_bf16") else "tf32") if use_tc else "f32", "data": "synthetic",
+            "vs_baseline": None, "dtype": dtype, "data": "synthetic",
             "config": {"workload": f"tetrapeptide forward-sim num_frames={T} crop={L}, {K} Euler steps, "
                                    f"batch {B} per GPU (BASELINE.json configs[1])",
                        "tokens_per_forward": N, "parallelism": f"dp{world} (independent trajectories, "
-                       "no data-path collective)", "l2": "working set (>4 GB activations per forward) "
+                       "no data-path collective)", "l2": "working set (>3 GB activations per forward) "
                        "far exceeds the 126 MB L2; no explicit flush needed",
                        "graph_replays": eng.get_option("graph_replays"),
-                       "gemm_path": ("tcgen05 " + ("bf16 operands (token GEMMs, attention P.V) / TF32 (attention Q.K^T), fp32 accumulate; "
-                                     "IPA key-frame trunk fp32" if eng.get_option("gemm_bf16") else "TF32"))
+                       "gemm_path": ("tcgen05, fp32 accumulate: token GEMMs " + {0: "TF32", 1: "bf16", 2: "fp16"}.get(gdt, "?")
+                                     + " operands, attention (generation 8) fp16 Q.K^T / P.V; IPA key-frame trunk fp32")
                                     if use_tc else "fp32 SIMT"},
             "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
-            "cpu_baseline": cpu_baseline, "torch_gpu_reference": torch_gpu,
+            "cpu_baseline": cpu_baseline, "torch_gpu_reference": torch_gpu, "extra_configs": extra,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

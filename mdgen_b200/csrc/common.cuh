@@ -114,6 +114,12 @@ __device__ __forceinline__ void store_operand4(void* base, size_t idx, float4 v,
   }
 }
 
+// 16-byte asynchronous global -> shared copy (LDGSTS, L2 only)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+
 __device__ __forceinline__ float gelu_erf(float x) {  // mdgen/model/layers.py:77-84
   return x * 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
 }

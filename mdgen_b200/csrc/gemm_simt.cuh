@@ -123,11 +123,6 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const float* __restrict_
 constexpr int SK_BM = 32, SK_BN = 64, SK_BK = 32, SK_PITCH = 36, SK_STAGES = 3;
 constexpr int SK_SMEM_BYTES = SK_STAGES * (SK_BM + SK_BN) * SK_PITCH * 4;
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-  uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
-}
-
 template <int MODE>
 __global__ void __launch_bounds__(128) gemm_skinny_kernel(const float* __restrict__ A, int lda,
                                                           const float* __restrict__ W, int ldw,

@@ -85,7 +85,7 @@ struct mdgen_handle {
   int64_t graph_launches_per_pair = 0, graph_replays = 0;
   bool trunk_precomputed = false;   // set by mdgen_sample_euler while the step loop runs
   int use_tc_attn = 1; // tcgen05 attention for sequences longer than 64 (needs use_tc)
-  int l4_variant = 0;   // S = 4 residue attention: 1 = shared-memory exchange kernel (experiment, see attention_simt.cuh)
+  int l4_variant = 1;   // S = 4 residue attention: 1 = warp-private shared-memory exchange (default), 0 = warp shuffles
 #ifdef MDGEN_NO_TC
   int attn_variant = 0;
 #else
@@ -434,7 +434,7 @@ int attention(mdgen_handle* h, cudaStream_t s, const float* qkv, const float* ma
 #endif
   if (sm.S == 4) {
     long long threads = sm.num_seq * 2 * 32;
-    if (h->l4_variant) attn_l4s_kernel<<<(unsigned)((sm.num_seq * 2 + 3) / 4), 128, 0, s>>>(p);
+    if (h->l4_variant == 1) attn_l4s_kernel<<<(unsigned)((sm.num_seq * 2 + 3) / 4), 128, 0, s>>>(p);
     else attn_l4_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(p);
   } else if (sm.S <= 64) {
     long long total = sm.num_seq * sm.S * kH;

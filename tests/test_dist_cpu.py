@@ -55,8 +55,9 @@ def test_two_rank_gloo_sharding_and_max_time():
 
 
 def test_reference_arm_under_torchrun_prints_one_line():
-    """bench.py --impl reference launched the way the driver launches it for N > 1: rank 0 alone runs the CPU
-    port on a bounded sample and prints ONE JSON line with the contract's keys; the other rank exits 0 silently."""
+    """bench.py --impl reference launched the way the driver launches it for N > 1: rank 0 alone runs the reference
+    (here, without a GPU, its CPU path on a bounded sample) and prints ONE JSON line with the contract's keys; the
+    other rank exits 0 silently."""
     import json
     import os
     import socket
@@ -76,5 +77,6 @@ def test_reference_arm_under_torchrun_prints_one_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["unit"] == "frames/s" and d["value"] > 0
     assert d["higher_is_better"] is True and d["gpu_launches"] == 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["config"]["device"] == "cpu" and d["ms_per_step"] > 0
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
