@@ -147,6 +147,19 @@ int mdgen_decode_atom14(mdgen_handle* h, int32_t B, int32_t T, int32_t L, const 
 int mdgen_featurize_atom14(mdgen_handle* h, int32_t B, int32_t L, const float* atom14, const int64_t* seqres,
                            float* rots, float* trans, float* torsions, float* torsion_mask, void* stream);
 
+/* Training / validation loss pieces (the forward half of Transport.training_losses,
+ * mdgen/transport/transport.py:138-223). All device pointers; `per` = elements per sample (T*L*D).
+ * Interpolant plan (mdgen/transport/path.py:118-135): xt = alpha(t) x1 + sigma(t) x0, ut = alpha'(t) x1 + sigma'(t) x0
+ * with per-sample t [B]; path 0 = GVP (path.py:173-191: sin / cos of pi t / 2), 1 = Linear (alpha = t, sigma = 1 - t). */
+int mdgen_flow_plan(mdgen_handle* h, int32_t B, int64_t per, int32_t path, const float* x1, const float* x0,
+                    const float* t, float* xt, float* ut, void* stream);
+/* loss[b] = mean_flat((pred - target)^2, mask) = sum((pred-target)^2 * mask) / sum(mask) over the non-batch dims
+ * (transport.py:13-17, :189). */
+int mdgen_masked_mse(mdgen_handle* h, int32_t B, int64_t per, const float* pred, const float* target,
+                     const float* mask, float* loss, void* stream);
+/* ExponentialMovingAverage.update for one tensor (mdgen/ema.py:41-50): stored -= (stored - param) * (1 - decay). */
+int mdgen_ema_update(mdgen_handle* h, float* stored, const float* param, int64_t n, float decay, void* stream);
+
 /* Introspection for tests / bench. */
 int mdgen_abi_version(void);
 /* number of kernel launches issued by this handle since creation (bench.py's gpu_launches) */

@@ -22,6 +22,7 @@ EXPORTS = [
     "mdgen_prep_batch", "mdgen_decode_atom14", "mdgen_abi_version", "mdgen_launch_count",
     "mdgen_set_option", "mdgen_get_option", "mdgen_profile_dump", "mdgen_debug_linear",
     "mdgen_set_featurize_tables", "mdgen_featurize_atom14",
+    "mdgen_flow_plan", "mdgen_masked_mse", "mdgen_ema_update",
 ]
 
 
@@ -72,6 +73,9 @@ def load_library():
     lib.mdgen_decode_atom14.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 6
     lib.mdgen_set_featurize_tables.argtypes = [C.c_void_p] + [C.c_void_p] * 4
     lib.mdgen_featurize_atom14.argtypes = [C.c_void_p, C.c_int32, C.c_int32] + [C.c_void_p] * 7
+    lib.mdgen_flow_plan.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_int32] + [C.c_void_p] * 6
+    lib.mdgen_masked_mse.argtypes = [C.c_void_p, C.c_int32, C.c_int64] + [C.c_void_p] * 5
+    lib.mdgen_ema_update.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p]
     lib.mdgen_launch_count.restype = C.c_int64
     lib.mdgen_launch_count.argtypes = [C.c_void_p]
     lib.mdgen_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
@@ -260,6 +264,35 @@ class Engine:
                                                     trans.data_ptr(), tors.data_ptr(), tmask.data_ptr(),
                                                     _stream()))
         return rots, trans, tors, tmask
+
+    # -- training / validation loss pieces ------------------------------------------------------------
+    def flow_plan(self, x1, x0, t, path_type="GVP"):
+        """xt, ut of the interpolant (mdgen/transport/path.py:118-135) with per-sample t [B]."""
+        x1, x0 = _f32(x1, "x1"), _f32(x0, "x0")
+        B = x1.shape[0]
+        t = _f32(t, "t").reshape(B)
+        per = x1.numel() // B
+        xt, ut = torch.empty_like(x1), torch.empty_like(x1)
+        self._check(self.lib.mdgen_flow_plan(self.h, B, per, {"GVP": 0, "Linear": 1}[path_type], x1.data_ptr(),
+                                             x0.data_ptr(), t.data_ptr(), xt.data_ptr(), ut.data_ptr(), _stream()))
+        return xt, ut
+
+    def masked_mse(self, pred, target, mask):
+        """mean_flat((pred - target)^2, mask) per sample (mdgen/transport/transport.py:13-17,189)."""
+        pred, target = _f32(pred, "pred"), _f32(target, "target")
+        mask = _f32(mask.expand_as(pred), "mask")
+        B = pred.shape[0]
+        loss = torch.empty(B, device=pred.device, dtype=torch.float32)
+        self._check(self.lib.mdgen_masked_mse(self.h, B, pred.numel() // B, pred.data_ptr(), target.data_ptr(),
+                                              mask.data_ptr(), loss.data_ptr(), _stream()))
+        return loss
+
+    def ema_update(self, stored, param, decay):
+        """stored <- stored - (stored - param) (1 - decay), in place (mdgen/ema.py:41-50)."""
+        assert stored.is_cuda and stored.is_contiguous() and stored.dtype == torch.float32
+        p = _f32(param, "param")
+        self._check(self.lib.mdgen_ema_update(self.h, stored.data_ptr(), p.data_ptr(), stored.numel(), float(decay),
+                                              _stream()))
 
     def decode_atom14(self, samples, start_rot, start_trans, seqres):
         B, T, L, D = samples.shape

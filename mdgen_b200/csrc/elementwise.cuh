@@ -368,6 +368,75 @@ __global__ void to_f16_kernel(const float* __restrict__ src, uint16_t* __restric
   dst[i] = (uint16_t)(pack_f16x2_rn(src[i], 0.f) & 0xFFFFu);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Training / validation loss pieces (mdgen/transport/transport.py:138-223)
+// Interpolant plan (mdgen/transport/path.py:118-135): xt = alpha(t) x1 + sigma(t) x0, ut = alpha'(t) x1 + sigma'(t) x0
+//   path 0 (GVP, path.py:173-191): alpha = sin(pi t / 2), sigma = cos(pi t / 2)      path 1 (Linear, :68-96 ICPlan): alpha = t, sigma = 1 - t
+// t is per sample; `per` = elements per sample. 128-bit accesses when per % 4 == 0.
+__global__ void flow_plan_kernel(const float* __restrict__ x1, const float* __restrict__ x0, const float* __restrict__ t,
+                                 float* __restrict__ xt, float* __restrict__ ut, long long per, long long n, int path) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i >= n) return;
+  const float tb = t[i / per];
+  float a, s, da, ds;
+  if (path == 0) {
+    const float ang = tb * 1.57079632679489661923f;
+    a = sinf(ang); s = cosf(ang);
+    da = 1.57079632679489661923f * s; ds = -1.57079632679489661923f * a;
+  } else {
+    a = tb; s = 1.0f - tb; da = 1.0f; ds = -1.0f;
+  }
+  if ((per & 3) == 0 && i + 3 < n) {
+    const float4 v1 = *reinterpret_cast<const float4*>(x1 + i), v0 = *reinterpret_cast<const float4*>(x0 + i);
+    *reinterpret_cast<float4*>(xt + i) = make_float4(a * v1.x + s * v0.x, a * v1.y + s * v0.y, a * v1.z + s * v0.z, a * v1.w + s * v0.w);
+    *reinterpret_cast<float4*>(ut + i) = make_float4(da * v1.x + ds * v0.x, da * v1.y + ds * v0.y, da * v1.z + ds * v0.z, da * v1.w + ds * v0.w);
+  } else {
+    for (long long j = i; j < i + 4 && j < n; ++j) {
+      const float tj = t[j / per];
+      float aj = a, sj = s, daj = da, dsj = ds;
+      if (tj != tb) {   // element group straddles two samples
+        if (path == 0) { const float g = tj * 1.57079632679489661923f; aj = sinf(g); sj = cosf(g); daj = 1.57079632679489661923f * sj; dsj = -1.57079632679489661923f * aj; }
+        else { aj = tj; sj = 1.0f - tj; }
+      }
+      xt[j] = aj * x1[j] + sj * x0[j];
+      ut[j] = daj * x1[j] + dsj * x0[j];
+    }
+  }
+}
+
+// mean_flat (transport.py:13-17) of the squared error (transport.py:189): one block per sample,
+//   loss[b] = sum_i (pred - target)^2 mask / sum_i mask     (fixed summation order: deterministic)
+__global__ void __launch_bounds__(1024) masked_mse_kernel(const float* __restrict__ pred, const float* __restrict__ target,
+                                                          const float* __restrict__ mask, float* __restrict__ loss, long long per) {
+  __shared__ float snum[32], sden[32];
+  const long long base = (long long)blockIdx.x * per;
+  float num = 0.f, den = 0.f;
+  for (long long i = threadIdx.x; i < per; i += blockDim.x) {
+    const float d = pred[base + i] - target[base + i], m = mask[base + i];
+    num = fmaf(d * d, m, num);
+    den += m;
+  }
+  num = warp_sum(num); den = warp_sum(den);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) { snum[w] = num; sden[w] = den; }
+  __syncthreads();
+  if (w == 0) {
+    num = lane < (int)(blockDim.x >> 5) ? snum[lane] : 0.f;
+    den = lane < (int)(blockDim.x >> 5) ? sden[lane] : 0.f;
+    num = warp_sum(num); den = warp_sum(den);
+    if (lane == 0) loss[blockIdx.x] = num / den;
+  }
+}
+
+// Exponential moving average of the parameters (mdgen/ema.py:41-50): stored -= (stored - param) * (1 - decay)
+__global__ void ema_update_kernel(float* __restrict__ stored, const float* __restrict__ param, long long n, float one_minus_decay) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float diff = stored[i] - param[i];
+  diff *= one_minus_decay;
+  stored[i] -= diff;
+}
+
 // RoPE tables for positions 0..n-1: cos/sin(pos * inv_freq[i]), i < 12
 // (fair-esm RotaryEmbedding; see oracle/ref_shims/esm/rotary_embedding.py).
 __global__ void rope_table_kernel(const float* __restrict__ inv_freq, float* __restrict__ cosT,

@@ -1031,6 +1031,41 @@ int mdgen_decode_atom14(mdgen_handle* h, int32_t B, int32_t T, int32_t L, const 
   return MDGEN_OK;
 }
 
+int mdgen_flow_plan(mdgen_handle* h, int32_t B, int64_t per, int32_t path, const float* x1, const float* x0,
+                    const float* t, float* xt, float* ut, void* stream) {
+  if (!h || !x1 || !x0 || !t || !xt || !ut || B <= 0 || per <= 0 || path < 0 || path > 1) {
+    if (h) h->err = "mdgen_flow_plan: bad argument";
+    return MDGEN_E_INVALID;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  ProfScope ps(h, s, "flow_plan");
+  const long long n = (long long)B * per;
+  flow_plan_kernel<<<(unsigned)((n / 4 + 256) / 256), 256, 0, s>>>(x1, x0, t, xt, ut, per, n, path);
+  CHECK_LAUNCH(h);
+  return MDGEN_OK;
+}
+
+int mdgen_masked_mse(mdgen_handle* h, int32_t B, int64_t per, const float* pred, const float* target,
+                     const float* mask, float* loss, void* stream) {
+  if (!h || !pred || !target || !mask || !loss || B <= 0 || per <= 0) {
+    if (h) h->err = "mdgen_masked_mse: bad argument";
+    return MDGEN_E_INVALID;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  ProfScope ps(h, s, "masked_mse");
+  masked_mse_kernel<<<(unsigned)B, 1024, 0, s>>>(pred, target, mask, loss, per);
+  CHECK_LAUNCH(h);
+  return MDGEN_OK;
+}
+
+int mdgen_ema_update(mdgen_handle* h, float* stored, const float* param, int64_t n, float decay, void* stream) {
+  if (!h || !stored || !param || n <= 0) { if (h) h->err = "mdgen_ema_update: bad argument"; return MDGEN_E_INVALID; }
+  cudaStream_t s = (cudaStream_t)stream;
+  ema_update_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(stored, param, n, 1.0f - decay);
+  CHECK_LAUNCH(h);
+  return MDGEN_OK;
+}
+
 int mdgen_debug_linear(mdgen_handle* h, const float* A, const float* W, const float* bias, int64_t M, int32_t N,
                        int32_t K, int32_t act, int32_t use_tc, float* out, void* stream) {
   if (!h || !A || !W || !out || M <= 0 || N <= 0 || K <= 0) return MDGEN_E_INVALID;

@@ -65,19 +65,45 @@ class Sampler:
 
 
 class Transport:
-    """Placeholder for `create_transport` (training losses are a 'next' row)."""
+    """Flow-matching transport of mdgen/transport/transport.py:77-258 for the one configuration the reference trains
+    (velocity prediction, GVP or Linear interpolant => train_eps = sample_eps = 0, transport.py:95-124).
+    `training_losses` is the FORWARD half of the training step (what `validation_step` and the loss of
+    `training_step` need): noise / time sampling in host code (same RNG calls as the reference, transport.py:126-136),
+    interpolant plan and masked MSE as CUDA kernels behind the C ABI (mdgen_flow_plan, mdgen_masked_mse), the
+    denoiser through mdgen_forward. The backward pass is a 'next' row."""
 
-    def __init__(self, args=None):
+    def __init__(self, args=None, path_type="GVP"):
         self.args = args
+        self.path_type = path_type
         self.train_eps = 0
         self.sample_eps = 0
 
-    def training_losses(self, *a, **k):
-        raise NotImplementedError("mdgen_b200: training path not implemented (SURVEY.md §8f-3)")
+    def sample(self, x1):
+        """== transport.py:126-136: x0 ~ N(0, I) like x1, t ~ U(0, 1) per sample (drawn on the host, then moved)."""
+        x0 = torch.randn_like(x1)
+        t = torch.rand((x1.shape[0],)).to(x1)
+        return t, x0, x1
+
+    def training_losses(self, model, x1, aatype1=None, mask=None, model_kwargs=None, t=None, x0=None):
+        """== transport.py:138-223 (non-design): returns {'t', 'pred', 'loss'} with loss [B] = mean_flat((v - ut)^2, mask).
+        `t` / `x0` are optional overrides of the random draws (parity tests)."""
+        if getattr(self.args, "design", False):
+            raise NotImplementedError("mdgen_b200: design-mode Dirichlet flow matching is a 'next' row (SURVEY.md §8f-4)")
+        model_kwargs = model_kwargs or {}
+        if t is None or x0 is None:
+            t_s, x0_s, _ = self.sample(x1)
+            t = t_s if t is None else t
+            x0 = x0_s if x0 is None else x0
+        eng = model.engine()
+        with torch.cuda.device(x1.device):
+            xt, ut = eng.flow_plan(x1, x0, t, self.path_type)                    # path.py:132-135
+            pred = model(xt, t, **model_kwargs)                                  # transport.py:174
+            loss = eng.masked_mse(pred, ut, mask if mask is not None else torch.ones_like(pred))   # :189
+        return {"t": t, "pred": pred, "loss": loss}
 
 
 def create_transport(args, path_type="GVP", prediction="velocity", loss_weight=None,
                      train_eps=None, sample_eps=None):
     if prediction != "velocity" or path_type not in ("GVP", "Linear"):
         raise NotImplementedError("only velocity prediction with GVP/Linear paths is supported")
-    return Transport(args)
+    return Transport(args, path_type)

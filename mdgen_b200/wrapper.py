@@ -8,12 +8,16 @@ libmdgen_b200 through the C ABI; this file is glue.
 """
 from __future__ import annotations
 
+import time
+from collections import defaultdict
+
 import torch
 import torch.nn as nn
 
 from .config import backfill_args, config_from_args
 from .model import LatentMDGenModel
 from .rigid import Rigid, Rotation
+from .ema import ExponentialMovingAverage
 from .transport import Sampler, create_transport
 
 DESIGN_IDX = [1, 2]      # mdgen/wrapper.py:30-32
@@ -61,6 +65,12 @@ class NewMDGenWrapper(_Base):
         self.transport = create_transport(args, args.path_type, args.prediction, None)
         self.transport_sampler = Sampler(self.transport)
         self.stage = "val"
+        self._log = defaultdict(list)                         # wrapper.py:52-55
+        self.last_log_time = time.time()
+        self.iter_step = 0
+        if args.ema:                                          # wrapper.py:204-208
+            self.ema = ExponentialMovingAverage(model=self.model, decay=args.ema_decay)
+            self.cached_weights = None
 
     # ------------------------------------------------------------------------------------------
     def prep_batch(self, batch):
@@ -145,15 +155,85 @@ class NewMDGenWrapper(_Base):
         new_batch["torsions"] = tors[:, None]
         return atom14, new_batch
 
-    # -- training hooks: kept as names; the backward path is a 'next' row -----
+    # -- training / validation surface (mdgen/wrapper.py:56-172, 367-403) ---------------------------------------
+    def log(self, key, data):
+        """== wrapper.py:56-63."""
+        if isinstance(data, torch.Tensor):
+            data = data.mean().item()
+        if self.stage == "train" or self.args.validate:
+            self._log["iter_" + key].append(data)
+        self._log[self.stage + "_" + key].append(data)
+
     def general_step(self, batch, stage="train"):
-        raise NotImplementedError("mdgen_b200: training step not implemented (SURVEY.md §8f-3)")
+        """== wrapper.py:367-403 (non-design): featurise, draw (t, x0), interpolate, run the denoiser, masked MSE.
+        The loss VALUE is computed by the CUDA path for both stages; it carries no autograd graph (backward kernels are a
+        'next' row), so `training_step` refuses to hand it to an optimiser."""
+        self.iter_step += 1
+        self.stage = stage
+        start1 = time.time()
+        prep = self.prep_batch(batch)
+        start = time.time()
+        out_dict = self.transport.training_losses(
+            model=self.model, x1=prep["latents"], aatype1=None, mask=prep["loss_mask"],
+            model_kwargs=prep["model_kwargs"])
+        self.log("model_dur", time.time() - start)
+        loss = out_dict["loss"]
+        self.log("loss", loss)
+        self.log("time", out_dict["t"])
+        self.log("dur", time.time() - self.last_log_time)
+        if "name" in batch:
+            self.log("name", ",".join(batch["name"]))
+        self.log("general_step_dur", time.time() - start1)
+        self.last_log_time = time.time()
+        return loss.mean()
 
     def training_step(self, batch, batch_idx):
-        return self.general_step(batch, stage="train")
+        raise NotImplementedError(
+            "mdgen_b200: the backward pass of the training step is not implemented (SURVEY.md §8f-3); the forward half "
+            "- general_step(batch, stage='val') / validation_step - runs on the CUDA path")
 
+    @torch.no_grad()
     def validation_step(self, batch, batch_idx):
-        return self.general_step(batch, stage="val")
+        """== wrapper.py:88-99."""
+        if self.args.ema:
+            if self.ema.device != self.device:
+                self.ema.to(self.device)
+            if self.cached_weights is None:
+                self.load_ema_weights()
+        loss = self.general_step(batch, stage="val")
+        self.validation_step_extra(batch, batch_idx)
+        return loss
+
+    def validation_step_extra(self, batch, batch_idx):
+        pass
+
+    def load_ema_weights(self):
+        """== wrapper.py:65-72."""
+        self.cached_weights = {k: v.detach().clone() for k, v in self.model.state_dict().items()}
+        self.model.load_state_dict(self.ema.state_dict()["params"])
+
+    def restore_cached_weights(self):
+        """== wrapper.py:74-77."""
+        self.model.load_state_dict(self.cached_weights)
+        self.cached_weights = None
+
+    def on_before_zero_grad(self, *args, **kwargs):
+        if self.args.ema:
+            self.ema.update(self.model)                       # wrapper.py:78-80
+
+    def on_validation_epoch_end(self):
+        if self.args.ema:
+            self.restore_cached_weights()                     # wrapper.py:107-110
+
+    def on_load_checkpoint(self, checkpoint):
+        if self.args.ema:
+            self.ema.load_state_dict(checkpoint["ema"])       # wrapper.py:120-124
+
+    def on_save_checkpoint(self, checkpoint):
+        if self.args.ema:                                     # wrapper.py:126-130
+            if self.cached_weights is not None:
+                self.restore_cached_weights()
+            checkpoint["ema"] = self.ema.state_dict()
 
     def configure_optimizers(self):
         cls = torch.optim.AdamW if self.args.adamW else torch.optim.Adam

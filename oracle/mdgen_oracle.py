@@ -451,8 +451,13 @@ def prep_batch(cfg, batch):
         cond_mask[:, ::cfg.cond_interval] = 1
     if cfg.inpainting:
         cond_mask[:, :, [0, 3]] = 1                                                   # COND_IDX :42,346
+    nfr = 14 if (cfg.tps_condition or cfg.inpainting) else 7
+    frame_lm = batch["mask"][..., None].expand(-1, -1, nfr)                          # :311, :318
+    tors_lm = batch["torsion_mask"][..., None].expand(-1, -1, -1, 2).reshape(B, L, 14)   # :312
+    loss_mask = torch.cat([frame_lm, tors_lm], -1)[:, None].expand(-1, T, -1, -1)     # :334-335
     return {
         "latents": latents,
+        "loss_mask": loss_mask,
         "start": (R[:, 0], tr[:, 0]),
         "end": (R[:, -1], tr[:, -1]),
         "mask": batch["mask"][:, None].expand(-1, T, -1),
@@ -566,3 +571,31 @@ def featurize_atom14(atom14, seqres):
     sc = sc / torch.sqrt((sc * sc).sum(-1, keepdim=True) + 1e-8)                                     # :185-194
     sc = sc * torch.tensor([1.0, 1.0, -1.0, 1.0, 1.0, 1.0, 1.0])[None, None, :, None]                # :196-201
     return R, t, sc, tmask
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Training / validation loss (forward half of the training step)
+def flow_plan(t, x0, x1, path_type="GVP"):
+    """ICPlan.plan — mdgen/transport/path.py:118-135 with GVPCPlan (:173-191) or the linear ICPlan (:68-96)."""
+    import math
+    tb = t.reshape(-1, *([1] * (x1.dim() - 1)))
+    if path_type == "GVP":
+        a, s = torch.sin(tb * math.pi / 2), torch.cos(tb * math.pi / 2)
+        da, ds = math.pi / 2 * torch.cos(tb * math.pi / 2), -math.pi / 2 * torch.sin(tb * math.pi / 2)
+    else:
+        a, s, da, ds = tb, 1 - tb, torch.ones_like(tb), -torch.ones_like(tb)
+    return a * x1 + s * x0, da * x1 + ds * x0
+
+
+def mean_flat(x, mask):
+    """mdgen/transport/transport.py:13-17."""
+    dims = list(range(1, x.dim()))
+    return torch.sum(x * mask, dim=dims) / torch.sum(mask, dim=dims)
+
+
+def training_losses(sd, cfg, x1, loss_mask, t, x0, path_type="GVP", **kw):
+    """Transport.training_losses (non-design) — mdgen/transport/transport.py:138-189 with the random draws (t, x0) of
+    Transport.sample (:126-136) passed in. Returns (loss [B], pred)."""
+    xt, ut = flow_plan(t, x0, x1, path_type)
+    pred = forward(sd, cfg, xt, t, **kw)
+    return mean_flat((pred - ut) ** 2, loss_mask), pred

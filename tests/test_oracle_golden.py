@@ -105,3 +105,27 @@ def test_featurize_oracle_matches_reference_golden(golden_dir):
         assert (t - torch.from_numpy(f[f"{name}/trans"])).abs().max() < 1e-6
         assert (sc - torch.from_numpy(f[f"{name}/torsions"])).abs().max() < 2e-5
         assert (m.numpy() == f[f"{name}/torsion_mask"]).all()
+
+
+TRAIN_CASES = ["sim_c1", "atlas_small", "upsampling", "tps", "inpaint", "stress"]
+
+
+@pytest.mark.parametrize("name", TRAIN_CASES)
+def test_oracle_training_loss_matches_reference_general_step(name, golden_dir):
+    """Forward half of the training step: the oracle's restatement of Transport.training_losses /
+    mean_flat / the GVP plan against the per-sample losses of the reference's own general_step(stage='val')
+    (tests/golden/gen_train_golden.py), fed with the (t, x0) the reference drew."""
+    import os
+
+    import numpy as np
+    torch.set_num_threads(8)
+    g = np.load(os.path.join(golden_dir, "train_loss.npz"))
+    case, args, cfg, sd, batch, zs, _ = load_case(name)
+    prep = O.prep_batch(cfg, batch)
+    kw = dict(mask=prep["mask"], start=prep["start"], end=prep["end"], x_cond=prep["x_cond"],
+              x_cond_mask=prep["x_cond_mask"], aatype=prep["aatype"])
+    with torch.no_grad():
+        loss, _ = O.training_losses(sd, cfg, prep["latents"], prep["loss_mask"], torch.from_numpy(g[f"{name}/t"]),
+                                    torch.from_numpy(g[f"{name}/x0"]), **kw)
+    assert max_rel(loss, g[f"{name}/loss"]) < 5e-5, (loss, g[f"{name}/loss"])
+    assert abs(float(loss.mean()) - float(g[f"{name}/loss_mean"])) < 5e-5 * float(g[f"{name}/loss_mean"])
