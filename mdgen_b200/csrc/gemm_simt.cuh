@@ -12,6 +12,8 @@ enum EpiMode : int {
   EPI_GELU = 1,        // out = gelu(acc + bias)                   (fc1, layers.py:84)
   EPI_RESID_GATE = 2,  // out = resid + gate[b] * (acc + bias)     (latent_model.py:462,476,481)
   EPI_RESID = 3,       // out = resid + (acc + bias)               (x + ipa(...), latent_model.py:372)
+  EPI_GATE = 4,        // out = gate[b] * (acc + bias): the gated branch output; the residual add is fused into the
+                       // LayerNorm kernel that reads the residual stream next (ln_mod_kernel, y_add)
 };
 
 struct Epilogue {
@@ -34,6 +36,7 @@ __device__ __forceinline__ float apply_epilogue(const Epilogue& ep, float acc, l
     v = ep.resid[(size_t)m * ep.ldo + n] + mr[ep.gate_off + n] * v;
   }
   if (MODE == EPI_RESID) v = ep.resid[(size_t)m * ep.ldo + n] + v;
+  if (MODE == EPI_GATE) v = mod_row(ep.mod, m)[ep.gate_off + n] * v;
   if (ep.round_out) v = round_operand(v, ep.round_out);
   return v;
 }

@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(128 + 32 * tc_epi_warps(MODE), 1) gemm_tc_kern
     const int rr0 = lane >> 3, c4 = lane & 7;
     // gate rows: base of the current step's modulation row (read once), + b * bstride rows per sample
     const float* gate_base = nullptr;
-    if (MODE == EPI_RESID_GATE)
+    if (MODE == EPI_RESID_GATE || MODE == EPI_GATE)
       gate_base = ep.mod.base + (size_t)(ep.mod.step_ptr ? *ep.mod.step_ptr : 0) * ep.mod.width + ep.gate_off;
     uint32_t it = 0;
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
@@ -367,6 +367,11 @@ __global__ void __launch_bounds__(128 + 32 * tc_epi_warps(MODE), 1) gemm_tc_kern
               a.z = res[itr].z + g.z * a.z; a.w = res[itr].w + g.w * a.w;
             }
             if (MODE == EPI_RESID) { a.x += res[itr].x; a.y += res[itr].y; a.z += res[itr].z; a.w += res[itr].w; }
+            if (MODE == EPI_GATE) {
+              const int bb = (int)(m / ep.mod.tokens_per_b) % ep.mod.bmod;
+              const float4 g = *reinterpret_cast<const float4*>(gate_base + (size_t)(bb * ep.mod.bstride) * ep.mod.width + n);
+              a.x *= g.x; a.y *= g.y; a.z *= g.z; a.w *= g.w;
+            }
             if (ep.round_out) { a.x = round_operand(a.x, ep.round_out); a.y = round_operand(a.y, ep.round_out); a.z = round_operand(a.z, ep.round_out); a.w = round_operand(a.w, ep.round_out); }
             if (BF16OUT) {
               uint2 pk;
@@ -514,6 +519,7 @@ inline int tc_gemm_launch(int mode, const void* A, int lda, const void* W, int l
       case EPI_GELU: return tc_launch_mode<EPI_GELU, false, false>(ta, tb, M, N, K, ep, s, grid, err);
       case EPI_RESID_GATE: return tc_launch_mode<EPI_RESID_GATE, false, false>(ta, tb, M, N, K, ep, s, grid, err);
       case EPI_RESID: return tc_launch_mode<EPI_RESID, false, false>(ta, tb, M, N, K, ep, s, grid, err);
+      case EPI_GATE: return tc_launch_mode<EPI_GATE, false, false>(ta, tb, M, N, K, ep, s, grid, err);
     }
   } else if (!out_bf16) {
     switch (mode) {
@@ -521,6 +527,7 @@ inline int tc_gemm_launch(int mode, const void* A, int lda, const void* W, int l
       case EPI_GELU: return tc_launch_mode<EPI_GELU, true, false>(ta, tb, M, N, K, ep, s, grid, err);
       case EPI_RESID_GATE: return tc_launch_mode<EPI_RESID_GATE, true, false>(ta, tb, M, N, K, ep, s, grid, err);
       case EPI_RESID: return tc_launch_mode<EPI_RESID, true, false>(ta, tb, M, N, K, ep, s, grid, err);
+      case EPI_GATE: return tc_launch_mode<EPI_GATE, true, false>(ta, tb, M, N, K, ep, s, grid, err);
     }
   } else {
     switch (mode) {

@@ -119,6 +119,8 @@ struct mdgen_handle {
   long long cap_op_bytes = 0;   // (tokens + 128) x element size the GEMM-operand activation buffers hold (2 = bf16, 4 = fp32 / TF32)
   int cap_modrows = 0;
   float *h = nullptr, *xn = nullptr, *qkv = nullptr, *att = nullptr, *hid = nullptr, *cond = nullptr;
+  float* ybuf = nullptr;   // gate * branch output of the out-proj / fc2 GEMMs when the residual add is fused into ln_mod
+  int fuse_resid_ln = 0;   // 1: residual add in ln_mod_kernel (EPI_GATE GEMM epilogues; measured neutral: the bytes only move); 0 (default): in the GEMM epilogue
   float *xi = nullptr, *xni = nullptr, *proj = nullptr, *cat = nullptr, *qkvi = nullptr, *atti = nullptr,
         *hidi = nullptr, *frot = nullptr, *ftrans = nullptr, *fmask = nullptr, *ipa_out = nullptr;
   float *tvals = nullptr, *sinus = nullptr, *h1 = nullptr, *st = nullptr, *mod = nullptr, *dt = nullptr;
@@ -297,11 +299,12 @@ int ensure_workspace(mdgen_handle* h, long long N, long long rows, int modrows) 
   const bool b16 = h->use_tc && h->gemm_bf16 && h->use_tc_attn && N >= h->tc_min_rows;
   const int elem = b16 ? 2 : 4;
   if (N > h->cap_tokens) {
-    float** bufs[] = {&h->h, &h->cond, &h->xbuf, &h->xbuf2};
+    float** bufs[] = {&h->h, &h->cond, &h->xbuf, &h->xbuf2, &h->ybuf};
     for (auto b : bufs) { dev_free(h, *b); *b = nullptr; }
     h->cap_tokens = 0;
     size_t n = (size_t)N + 128;
     TRY(dev_alloc_t(h, &h->h, n * kC));
+    TRY(dev_alloc_t(h, &h->ybuf, n * kC));
     TRY(dev_alloc_t(h, &h->cond, n * kC));
     TRY(dev_alloc_t(h, &h->xbuf, n * 28));
     TRY(dev_alloc_t(h, &h->xbuf2, n * 28));
@@ -447,11 +450,11 @@ int attention(mdgen_handle* h, cudaStream_t s, const float* qkv, const float* ma
   return MDGEN_OK;
 }
 
-int ln_mod(mdgen_handle* h, cudaStream_t s, const float* x, float* y, const ModRef& mod, int shift_off,
-           int scale_off, long long N, int rmode) {
+int ln_mod(mdgen_handle* h, cudaStream_t s, float* x, float* y, const ModRef& mod, int shift_off,
+           int scale_off, long long N, int rmode, const float* y_add = nullptr) {
   ProfScope ps(h, s, "ln_mod");
   unsigned blocks = (unsigned)((N * 32 + 255) / 256);
-  ln_mod_kernel<<<blocks, 256, 0, s>>>(x, y, mod, shift_off, scale_off, N, rmode);
+  ln_mod_kernel<<<blocks, 256, 0, s>>>(x, y_add, y, mod, shift_off, scale_off, N, rmode);
   CHECK_LAUNCH(h);
   return MDGEN_OK;
 }
@@ -596,26 +599,37 @@ int run_step(mdgen_handle* h, cudaStream_t s, const mdgen_cond* c, const float* 
     const void* wo_t = pick(w.mha_t.wo_f16, w.mha_t.wo_b16, w.mha_t.wo_bf, w.mha_t.wo_tc, 2);
     const void* w1x = pick(w.w1_f16, w.w1_b16, w.w1_bf, w.w1_tc, 1);
     const void* w2x = pick(w.w2_f16, w.w2_b16, w.w2_bf, w.w2_tc, 1);
+    // The gated branch outputs (out-proj, fc2) either add into the residual stream in their GEMM epilogue
+    // (EPI_RESID_GATE) or - default on the tensor-core path - are stored as gate * branch (EPI_GATE) and added by the
+    // next ln_mod_kernel, which reads the residual stream anyway. The last fc2 always adds in its epilogue (the
+    // final layer's LayerNorm lives in final_kernel).
+    const bool fuse = rt && h->fuse_resid_ln;
+    auto branch_out = [&](const float* A, int lda, const float* W, const void* Wx, int ldw, int K, const float* bias,
+                          int gate_off, const char* tag, bool defer) -> int {
+      if (defer) {
+        Epilogue e = make_epi(bias, h->ybuf, kC);
+        e.mod = modm; e.gate_off = gate_off;
+        return gemm(h, s, EPI_GATE, A, lda, W, Wx, ldw, N, kC, K, e, tag, hf);
+      }
+      return gemm(h, s, EPI_RESID_GATE, A, lda, W, Wx, ldw, N, kC, K, make_epi_gate(bias, h->h, kC, modm, gate_off), tag, hf);
+    };
     // residue attention (over L)
-    TRY(ln_mod(h, s, h->h, h->xn, modm, off + 0, off + kC, N, rm_attn));
+    TRY(ln_mod(h, s, h->h, h->xn, modm, off + 0, off + kC, N, rm_attn, (fuse && i > 0) ? h->ybuf : nullptr));
     TRY(gemm(h, s, EPI_STORE, h->xn, kC, w.mha_l.wqkv, wqkv_l, kC, N, kQKV, kC,
              make_epi(w.mha_l.bqkv, h->qkv, kQKV, (h->emu_bf16 & 4) ? 2 : 0), "gemm_qkv", hf, bfq));
     TRY(attention(h, s, h->qkv, c->mask, w.mha_l, h->att, sml, rm_attn, "mha_l", true, hfq));
-    TRY(gemm(h, s, EPI_RESID_GATE, h->att, kC, w.mha_l.wo, wo_l, kC, N, kC, kC,
-             make_epi_gate(w.mha_l.bo, h->h, kC, modm, off + 2 * kC), "gemm_out", hf));
+    TRY(branch_out(h->att, kC, w.mha_l.wo, wo_l, kC, kC, w.mha_l.bo, off + 2 * kC, "gemm_out", fuse));
     // time attention (over T)
-    TRY(ln_mod(h, s, h->h, h->xn, modm, off + 3 * kC, off + 4 * kC, N, rm_attn));
+    TRY(ln_mod(h, s, h->h, h->xn, modm, off + 3 * kC, off + 4 * kC, N, rm_attn, fuse ? h->ybuf : nullptr));
     TRY(gemm(h, s, EPI_STORE, h->xn, kC, w.mha_t.wqkv, wqkv_t, kC, N, kQKV, kC,
              make_epi(w.mha_t.bqkv, h->qkv, kQKV, (h->emu_bf16 & 4) ? 2 : 0), "gemm_qkv", hf, bfq));
     TRY(attention(h, s, h->qkv, c->mask, w.mha_t, h->att, smt, rm_attn, "mha_t", true, hfq));
-    TRY(gemm(h, s, EPI_RESID_GATE, h->att, kC, w.mha_t.wo, wo_t, kC, N, kC, kC,
-             make_epi_gate(w.mha_t.bo, h->h, kC, modm, off + 5 * kC), "gemm_out", hf));
-    // MLP (hidden activations are bf16 in bf16 mode: written by fc1, read only by fc2)
-    TRY(ln_mod(h, s, h->h, h->xn, modm, off + 6 * kC, off + 7 * kC, N, rm_mlp));
+    TRY(branch_out(h->att, kC, w.mha_t.wo, wo_t, kC, kC, w.mha_t.bo, off + 5 * kC, "gemm_out", fuse));
+    // MLP (hidden activations are 16-bit on the default path: written by fc1, read only by fc2)
+    TRY(ln_mod(h, s, h->h, h->xn, modm, off + 6 * kC, off + 7 * kC, N, rm_mlp, fuse ? h->ybuf : nullptr));
     TRY(gemm(h, s, EPI_GELU, h->xn, kC, w.w1, w1x, kC, N, kFF, kC, make_epi(w.b1, h->hid, kFF, bf ? 0 : rm_mlp),
              "gemm_fc1", hf, bf));
-    TRY(gemm(h, s, EPI_RESID_GATE, h->hid, kFF, w.w2, w2x, kFF, N, kC, kFF,
-             make_epi_gate(w.b2, h->h, kC, modm, off + 8 * kC), "gemm_fc2", hf));
+    TRY(branch_out(h->hid, kFF, w.w2, w2x, kFF, kFF, w.b2, off + 8 * kC, "gemm_fc2", fuse && i + 1 < n));
   }
 
   // ---------------- final layer (+ Euler update)
@@ -1124,6 +1138,7 @@ int mdgen_set_option(mdgen_handle* h, const char* key, int64_t value) {
   else if (k == "emu_bf16") h->emu_bf16 = (int)value;
   else if (k == "gemm_bf16") h->gemm_bf16 = (int)value;
   else if (k == "use_graph") h->use_graph = (int)value;
+  else if (k == "fuse_resid_ln") h->fuse_resid_ln = (int)value;
   else if (k == "graph_max_tokens") h->graph_max_tokens = value;
   else if (k == "profile") {
     h->profile = (int)value;
@@ -1145,6 +1160,7 @@ int64_t mdgen_get_option(const mdgen_handle* h, const char* key) {
   if (k == "l4_variant") return h->l4_variant;
   if (k == "gemm_bf16") return h->gemm_bf16;
   if (k == "use_graph") return h->use_graph;
+  if (k == "fuse_resid_ln") return h->fuse_resid_ln;
   if (k == "graph_replays") return h->graph_replays;
   if (k == "profile") return h->profile;
   if (k == "modw") return h->modw;
