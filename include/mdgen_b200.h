@@ -160,6 +160,17 @@ int mdgen_masked_mse(mdgen_handle* h, int32_t B, int64_t per, const float* pred,
 /* ExponentialMovingAverage.update for one tensor (mdgen/ema.py:41-50): stored -= (stored - param) * (1 - decay). */
 int mdgen_ema_update(mdgen_handle* h, float* stored, const float* param, int64_t n, float decay, void* stream);
 
+/* Runge-Kutta plumbing of the adaptive dopri5 sampler (the reference's default sampling_method: torchdiffeq.odeint
+ * behind mdgen/transport/integrators.py:106-113). out[n] = (y ? y : 0) + scale * sum_{i<nk} coeffs[i] * ks[i]
+ * (nk <= 8; coeffs host floats, ks host array of device pointers): stage, solution, error and dense-output
+ * combinations in one pass over the state. */
+int mdgen_lincomb(mdgen_handle* h, int64_t n, const float* y, float scale, const float* coeffs /*host*/,
+                  const float* const* ks /*host array of device pointers*/, int32_t nk, float* out, void* stream);
+/* ratio (host float out) = sqrt(mean((err / (atol + rtol * max(|y0|, |y1|)))^2)): torchdiffeq's mixed-tolerance RMS
+ * error norm over the whole state (fixed summation order). Synchronises the stream (the step controller needs it). */
+int mdgen_rk_error_ratio(mdgen_handle* h, int64_t n, const float* err, const float* y0, const float* y1,
+                         float rtol, float atol, float* ratio /*host*/, void* stream);
+
 /* Introspection for tests / bench. */
 int mdgen_abi_version(void);
 /* number of kernel launches issued by this handle since creation (bench.py's gpu_launches) */
@@ -174,6 +185,8 @@ int64_t mdgen_launch_count(const mdgen_handle* h);
  *   "l4_variant"    0 (default) shuffle-based S = 4 residue attention, 1 = shared-memory exchange kernel
  *   "tc_min_rows"   GEMMs with fewer rows (the IPA key-frame trunk) stay on the exact-fp32 skinny GEMM (1024)
  *   "use_graph", "graph_max_tokens"   CUDA-graph replay of the Euler steps for launch-bound workloads (1, 65536)
+ *   "reuse_cond"    1: mdgen_forward keeps the conditioning embedding of its previous call (same cond object and
+ *                   shapes: the stages of one adaptive ODE solve); the caller resets it to 0 afterwards
  *   "emu_bf16"      precision experiments (tools/diag_precision.py);  "profile" 1 = per-family CUDA-event timing
  * Unknown keys return MDGEN_E_INVALID. */
 int mdgen_set_option(mdgen_handle* h, const char* key, int64_t value);

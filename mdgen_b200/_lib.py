@@ -22,7 +22,7 @@ EXPORTS = [
     "mdgen_prep_batch", "mdgen_decode_atom14", "mdgen_abi_version", "mdgen_launch_count",
     "mdgen_set_option", "mdgen_get_option", "mdgen_profile_dump", "mdgen_debug_linear",
     "mdgen_set_featurize_tables", "mdgen_featurize_atom14",
-    "mdgen_flow_plan", "mdgen_masked_mse", "mdgen_ema_update",
+    "mdgen_flow_plan", "mdgen_masked_mse", "mdgen_ema_update", "mdgen_lincomb", "mdgen_rk_error_ratio",
 ]
 
 
@@ -76,6 +76,10 @@ def load_library():
     lib.mdgen_flow_plan.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_int32] + [C.c_void_p] * 6
     lib.mdgen_masked_mse.argtypes = [C.c_void_p, C.c_int32, C.c_int64] + [C.c_void_p] * 5
     lib.mdgen_ema_update.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p]
+    lib.mdgen_lincomb.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_int32,
+                                  C.c_void_p, C.c_void_p]
+    lib.mdgen_rk_error_ratio.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
+                                         C.c_float, C.c_void_p, C.c_void_p]
     lib.mdgen_launch_count.restype = C.c_int64
     lib.mdgen_launch_count.argtypes = [C.c_void_p]
     lib.mdgen_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
@@ -293,6 +297,26 @@ class Engine:
         p = _f32(param, "param")
         self._check(self.lib.mdgen_ema_update(self.h, stored.data_ptr(), p.data_ptr(), stored.numel(), float(decay),
                                               _stream()))
+
+    # -- Runge-Kutta plumbing of the adaptive sampler ------------------------------------------------
+    def lincomb(self, y, scale, coeffs, ks):
+        """(y or 0) + scale * sum_i coeffs[i] * ks[i]  in one pass (<= 8 terms)."""
+        ks = [_f32(k, "k") for k in ks]
+        n = ks[0].numel()
+        yy = _f32(y, "y") if y is not None else None
+        out = torch.empty_like(ks[0])
+        cf = (C.c_float * len(ks))(*[float(c) for c in coeffs])
+        ptrs = (C.c_void_p * len(ks))(*[k.data_ptr() for k in ks])
+        self._check(self.lib.mdgen_lincomb(self.h, n, yy.data_ptr() if yy is not None else None, float(scale), cf, ptrs,
+                                           len(ks), out.data_ptr(), _stream()))
+        return out
+
+    def rk_error_ratio(self, err, y0, y1, rtol, atol) -> float:
+        err, y0, y1 = _f32(err, "err"), _f32(y0, "y0"), _f32(y1, "y1")
+        r = C.c_float(0.0)
+        self._check(self.lib.mdgen_rk_error_ratio(self.h, err.numel(), err.data_ptr(), y0.data_ptr(), y1.data_ptr(),
+                                                  float(rtol), float(atol), C.byref(r), _stream()))
+        return float(r.value)
 
     def decode_atom14(self, samples, start_rot, start_trans, seqres):
         B, T, L, D = samples.shape

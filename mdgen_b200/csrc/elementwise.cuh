@@ -450,6 +450,68 @@ __global__ void ema_update_kernel(float* __restrict__ stored, const float* __res
   stored[i] -= diff;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Runge-Kutta plumbing of the adaptive dopri5 sampler (mdgen_b200/ode.py; torchdiffeq's rk_common): stage / solution /
+// error / interpolant combinations  out = (y ? y : 0) + scale * sum_i c_i k_i  over up to 8 tensors in ONE pass, and the
+// mixed-tolerance RMS error ratio  sqrt(mean((err / (atol + rtol max(|y0|, |y1|)))^2))  as a fixed-order two-stage
+// reduction (deterministic).
+struct LinComb {
+  const float* k[8];
+  float c[8];
+  int nk;
+};
+__global__ void lincomb_kernel(const float* __restrict__ y, float scale, LinComb lc, float* __restrict__ out, long long n) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i >= n) return;
+  if (i + 3 < n) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (j < lc.nk) {
+        const float4 v = *reinterpret_cast<const float4*>(lc.k[j] + i);
+        acc.x = fmaf(lc.c[j], v.x, acc.x); acc.y = fmaf(lc.c[j], v.y, acc.y);
+        acc.z = fmaf(lc.c[j], v.z, acc.z); acc.w = fmaf(lc.c[j], v.w, acc.w);
+      }
+    float4 b = y ? *reinterpret_cast<const float4*>(y + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(out + i) = make_float4(fmaf(scale, acc.x, b.x), fmaf(scale, acc.y, b.y),
+                                                      fmaf(scale, acc.z, b.z), fmaf(scale, acc.w, b.w));
+  } else {
+    for (long long e = i; e < n; ++e) {
+      float acc = 0.f;
+      for (int j = 0; j < lc.nk; ++j) acc = fmaf(lc.c[j], lc.k[j][e], acc);
+      out[e] = fmaf(scale, acc, y ? y[e] : 0.f);
+    }
+  }
+}
+constexpr int kErrBlocks = 512;
+__global__ void __launch_bounds__(256) rk_error_partial_kernel(const float* __restrict__ err, const float* __restrict__ y0,
+                                                               const float* __restrict__ y1, float rtol, float atol,
+                                                               double* __restrict__ partial, long long n) {
+  __shared__ double sh[8];
+  double acc = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float tol = atol + rtol * fmaxf(fabsf(y0[i]), fabsf(y1[i]));
+    const float r = err[i] / tol;
+    acc += (double)r * (double)r;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += sh[w];
+    partial[blockIdx.x] = t;
+  }
+}
+__global__ void rk_error_final_kernel(const double* __restrict__ partial, int nblocks, long long n, float* __restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double t = 0.0;
+    for (int b = 0; b < nblocks; ++b) t += partial[b];
+    out[0] = (float)sqrt(t / (double)n);
+  }
+}
+
 // RoPE tables for positions 0..n-1: cos/sin(pos * inv_freq[i]), i < 12
 // (fair-esm RotaryEmbedding; see oracle/ref_shims/esm/rotary_embedding.py).
 __global__ void rope_table_kernel(const float* __restrict__ inv_freq, float* __restrict__ cosT,

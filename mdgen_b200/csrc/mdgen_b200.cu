@@ -128,6 +128,10 @@ struct mdgen_handle {
   uint8_t* attn_scratch = nullptr;           // UMMA-ready key-tile images of the tcgen05 attention
   size_t attn_scratch_bytes = 0;
   int* step = nullptr;
+  int reuse_cond = 0;          // mdgen_forward: keep h->cond of the previous call (stages of one adaptive ODE solve)
+  long long cond_tokens = 0;   // tokens h->cond was built for
+  double* err_partial = nullptr;
+  float* err_out = nullptr;
 };
 
 namespace {
@@ -895,7 +899,9 @@ int mdgen_forward(mdgen_handle* h, const float* x, const float* t, const mdgen_c
   TRY(prepare_call(h, s, cond, cond ? cond->B : 0));
   CUDA_TRY(h, cudaMemcpyAsync(h->tvals, t, (size_t)cond->B * sizeof(float), cudaMemcpyDeviceToDevice, s));
   TRY(build_mod_table(h, s, cond->B));
-  TRY(build_cond(h, s, cond));
+  const long long ntok = (long long)cond->B * cond->T * cond->L;
+  if (!(h->reuse_cond && h->cond_tokens == ntok)) TRY(build_cond(h, s, cond));
+  h->cond_tokens = ntok;
   return run_step(h, s, cond, x, out, /*euler=*/false, nullptr, /*bstride=*/1);
 }
 
@@ -916,6 +922,7 @@ int mdgen_sample_euler(mdgen_handle* h, const float* zs, const float* t_grid, in
   CUDA_TRY(h, cudaStreamSynchronize(s));  // dt (host vector) must be consumed before it goes out of scope
   TRY(build_mod_table(h, s, K));
   TRY(build_cond(h, s, cond));
+  h->cond_tokens = 0;
   if (hoist) TRY(run_ipa_trunk(h, s, cond, K, nullptr, 0));
   h->trunk_precomputed = hoist;
   step_set_kernel<<<1, 1, 0, s>>>(h->step, 0);
@@ -1080,6 +1087,40 @@ int mdgen_ema_update(mdgen_handle* h, float* stored, const float* param, int64_t
   return MDGEN_OK;
 }
 
+int mdgen_lincomb(mdgen_handle* h, int64_t n, const float* y, float scale, const float* coeffs,
+                  const float* const* ks, int32_t nk, float* out, void* stream) {
+  if (!h || !out || n <= 0 || nk < 0 || nk > 8 || (nk > 0 && (!coeffs || !ks))) {
+    if (h) h->err = "mdgen_lincomb: bad argument";
+    return MDGEN_E_INVALID;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  LinComb lc;
+  lc.nk = 0;
+  for (int i = 0; i < nk; ++i)
+    if (coeffs[i] != 0.f) { lc.k[lc.nk] = ks[i]; lc.c[lc.nk] = coeffs[i]; ++lc.nk; }
+  for (int i = lc.nk; i < 8; ++i) { lc.k[i] = nullptr; lc.c[i] = 0.f; }
+  lincomb_kernel<<<(unsigned)((n / 4 + 256) / 256), 256, 0, s>>>(y, scale, lc, out, n);
+  CHECK_LAUNCH(h);
+  return MDGEN_OK;
+}
+
+int mdgen_rk_error_ratio(mdgen_handle* h, int64_t n, const float* err, const float* y0, const float* y1,
+                         float rtol, float atol, float* ratio, void* stream) {
+  if (!h || !err || !y0 || !y1 || !ratio || n <= 0) { if (h) h->err = "mdgen_rk_error_ratio: bad argument"; return MDGEN_E_INVALID; }
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!h->err_partial) {
+    TRY(dev_alloc_t(h, &h->err_partial, kErrBlocks));
+    TRY(dev_alloc_t(h, &h->err_out, 4));
+  }
+  rk_error_partial_kernel<<<kErrBlocks, 256, 0, s>>>(err, y0, y1, rtol, atol, h->err_partial, n);
+  CHECK_LAUNCH(h);
+  rk_error_final_kernel<<<1, 32, 0, s>>>(h->err_partial, kErrBlocks, n, h->err_out);
+  CHECK_LAUNCH(h);
+  CUDA_TRY(h, cudaMemcpyAsync(ratio, h->err_out, sizeof(float), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(h, cudaStreamSynchronize(s));
+  return MDGEN_OK;
+}
+
 int mdgen_debug_linear(mdgen_handle* h, const float* A, const float* W, const float* bias, int64_t M, int32_t N,
                        int32_t K, int32_t act, int32_t use_tc, float* out, void* stream) {
   if (!h || !A || !W || !out || M <= 0 || N <= 0 || K <= 0) return MDGEN_E_INVALID;
@@ -1139,6 +1180,7 @@ int mdgen_set_option(mdgen_handle* h, const char* key, int64_t value) {
   else if (k == "gemm_bf16") h->gemm_bf16 = (int)value;
   else if (k == "use_graph") h->use_graph = (int)value;
   else if (k == "fuse_resid_ln") h->fuse_resid_ln = (int)value;
+  else if (k == "reuse_cond") { h->reuse_cond = (int)value; if (!value) h->cond_tokens = 0; }
   else if (k == "graph_max_tokens") h->graph_max_tokens = value;
   else if (k == "profile") {
     h->profile = (int)value;

@@ -58,8 +58,26 @@ class Sampler:
                 return owner.forward_inference(y, tb, **kw)
 
             self.last_stats = {}
-            return _LastOnly(dopri5_integrate(rhs, x, t_grid.tolist(), rtol=rtol, atol=atol,
-                                              last_only=True, stats=self.last_stats))
+            eng = owner.engine() if (hasattr(owner, "engine") and x.is_cuda) else None
+            if eng is None:          # (host-side tests of the sampler surface drive a plain callable)
+                return _LastOnly(dopri5_integrate(rhs, x, t_grid.tolist(), rtol=rtol, atol=atol,
+                                                  last_only=True, stats=self.last_stats))
+            first = [True]
+
+            def rhs_cached(t, y):
+                # the conditioning embedding does not depend on (t, y): built by the first stage, kept by the others
+                out = rhs(t, y)
+                if first[0]:
+                    first[0] = False
+                    eng.set_option("reuse_cond", 1)
+                return out
+
+            try:
+                with torch.cuda.device(x.device):
+                    return _LastOnly(dopri5_integrate(rhs_cached, x, t_grid.tolist(), rtol=rtol, atol=atol,
+                                                      last_only=True, stats=self.last_stats, engine=eng))
+            finally:
+                eng.set_option("reuse_cond", 0)
 
         return sample
 

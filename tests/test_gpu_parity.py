@@ -495,3 +495,34 @@ def test_ema_update_kernel_and_checkpoint_hooks():
     assert m.cached_weights is not None
     m.on_validation_epoch_end()                   # ... and restores the trained ones
     assert m.cached_weights is None
+
+
+def test_rk_kernels_match_torch_and_residual_fusion_option():
+    """mdgen_lincomb / mdgen_rk_error_ratio (the adaptive sampler's stage combinations and error norm) against torch,
+    and the `fuse_resid_ln` option (residual add inside ln_mod_kernel, EPI_GATE GEMM epilogues) against the default."""
+    from mdgen_b200._lib import Engine
+    from mdgen_b200.config import config_from_args, default_args
+    eng = Engine(config_from_args(default_args(sim_condition=True, prepend_ipa=True, abs_pos_emb=True, crop=4)))
+    g = torch.Generator(device="cuda").manual_seed(9)
+    n = 2 * 37 * 4 * 21 + 3
+    ks = [torch.randn(n, device="cuda", generator=g) for _ in range(7)]
+    y = torch.randn(n, device="cuda", generator=g)
+    cf = [0.3, 0.0, -1.25, 2.0, 0.5, -0.125, 1.0 / 60]
+    out = eng.lincomb(y, 0.37, cf, ks)
+    ref = y.double() + 0.37 * sum(c * k.double() for c, k in zip(cf, ks))
+    assert max_rel(out.cpu(), ref.cpu()) < 1e-6
+    out0 = eng.lincomb(None, 1.0, cf[:3], ks[:3])
+    assert max_rel(out0.cpu(), sum(c * k.double() for c, k in zip(cf[:3], ks[:3])).cpu()) < 1e-6
+    r = eng.rk_error_ratio(ks[0], ks[1], ks[2], 1e-3, 1e-6)
+    tol = 1e-6 + 1e-3 * torch.maximum(ks[1].abs(), ks[2].abs()).double()
+    assert abs(r - float(((ks[0].double() / tol) ** 2).mean().sqrt())) < 1e-5 * r
+    # residual-add fusion option
+    case, args, cfg, sd, batch, zs, gold = load_case("stress")
+    m = _wrapper(args, sd, "fp16")
+    kw = m.prep_batch(_dev(batch))["model_kwargs"]
+    t = torch.tensor(case["t_fwd"]).cuda()
+    v0 = m.model.forward_inference(zs.cuda(), t, **kw)
+    m.model.engine().set_option("fuse_resid_ln", 1)
+    v1 = m.model.forward_inference(zs.cuda(), t, **kw)
+    assert max_rel(v1.cpu(), v0.cpu()) < 5e-4      # (one extra fp32 rounding per branch, amplified by the stress weights)
+    assert max_rel(v1.cpu(), gold["v"]) < TOL
