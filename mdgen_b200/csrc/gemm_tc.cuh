@@ -39,7 +39,7 @@ constexpr int TC_EPI_PITCH = 36;                // floats per staged row (144 B:
 // are instruction-issue bound and fit 128 registers
 constexpr int TC_EPI_WARPS_MAX = 12;
 constexpr int TC_EPI_BYTES = TC_EPI_WARPS_MAX * 32 * TC_EPI_PITCH * 4;
-__host__ __device__ constexpr int tc_epi_warps(int mode) { return (mode == EPI_RESID_GATE || mode == EPI_RESID) ? 8 : 12; }
+__host__ __device__ constexpr int tc_epi_warps(int mode) { return 12; }
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
 constexpr int TC_B_BYTES = TC_BN * TC_BK * 4;   // 24 KB
 constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
@@ -165,6 +165,56 @@ __device__ __forceinline__ float gelu_fast(float x) {
   const float erf_abs = fmaf(-poly, e, 1.0f);
   const float erf_v = copysignf(erf_abs, x);
   return 0.5f * x * (1.0f + erf_v);
+}
+
+// The same erf-GELU for two values at once with Blackwell's packed fp32x2 arithmetic (one issue slot per pair for
+// every multiply / FMA; the fc1 epilogue is issue bound): identical operations and rounding as gelu_fast per element.
+__device__ __forceinline__ uint64_t pk2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__host__ __device__ constexpr uint64_t splat2(uint32_t bits) { return ((uint64_t)bits << 32) | bits; }
+__device__ __forceinline__ void gelu_fast2(float& x0, float& x1) {
+  constexpr uint64_t kOne = splat2(0x3F800000u), kP = splat2(0x3EA7BA05u) /*0.3275911*/,
+                     kA5 = splat2(0x3F87DC22u) /*1.061405429*/, kA4 = splat2(0xBFBA00E3u) /*-1.453152027*/,
+                     kA3 = splat2(0x3FB5F0E3u) /*1.421413741*/, kA2 = splat2(0xBE91A98Eu) /*-0.284496736*/,
+                     kA1 = splat2(0x3E827906u) /*0.254829592*/, kNegL2e = splat2(0xBFB8AA3Bu) /*-1.4426950408889634*/,
+                     kHalf = splat2(0x3F000000u);
+  const float z0 = fabsf(x0) * 0.70710678118654752440f, z1 = fabsf(x1) * 0.70710678118654752440f;
+  const uint64_t z = pk2(z0, z1);
+  float d0, d1;
+  upk2(fma2(kP, z, kOne), d0, d1);
+  float t0, t1;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
+  const uint64_t t = pk2(t0, t1);
+  uint64_t poly = fma2(kA5, t, kA4);
+  poly = fma2(poly, t, kA3);
+  poly = fma2(poly, t, kA2);
+  poly = fma2(poly, t, kA1);
+  poly = mul2(poly, t);
+  float a0, a1;
+  upk2(mul2(mul2(z, z), kNegL2e), a0, a1);           // (-z) * z * log2(e) == -(z * z) * log2(e) up to the sign bit
+  float e0, e1;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
+  float p0, p1;
+  upk2(poly, p0, p1);
+  const float erf0 = copysignf(fmaf(-p0, e0, 1.0f), x0), erf1 = copysignf(fmaf(-p1, e1, 1.0f), x1);
+  const uint64_t hx = mul2(kHalf, pk2(x0, x1));
+  upk2(fma2(hx, pk2(erf0, erf1), hx), x0, x1);       // 0.5 x (1 + erf)
 }
 
 // ---- vectorised epilogue on 4 consecutive columns ------------------------------------------------
@@ -359,7 +409,7 @@ __global__ void __launch_bounds__(128 + 32 * tc_epi_warps(MODE), 1) gemm_tc_kern
           float4 a = *reinterpret_cast<const float4*>(stg + rr * TC_EPI_PITCH + 4 * c4);
           if (m < M) {
             a.x += bias4.x; a.y += bias4.y; a.z += bias4.z; a.w += bias4.w;
-            if (MODE == EPI_GELU) { a.x = gelu_fast(a.x); a.y = gelu_fast(a.y); a.z = gelu_fast(a.z); a.w = gelu_fast(a.w); }
+            if (MODE == EPI_GELU) { gelu_fast2(a.x, a.y); gelu_fast2(a.z, a.w); }
             if (MODE == EPI_RESID_GATE) {
               const int bb = (int)(m / ep.mod.tokens_per_b) % ep.mod.bmod;
               const float4 g = *reinterpret_cast<const float4*>(gate_base + (size_t)(bb * ep.mod.bstride) * ep.mod.width + n);

@@ -16,3 +16,8 @@ kw = m.prep_batch({k: v.cuda() for k, v in synthetic_batch(B, T, L, seed=1, vary
 zs = synthetic_noise(B, T, L, m.latent_dim, seed=2).cuda()
 m.model.sample_euler(zs, euler_time_grid(100)[:2], **kw)
 torch.cuda.synchronize()
+# second call between cudaProfilerStart/Stop: `ncu --profile-from-start off` then sees exactly one sampling call
+torch.cuda.profiler.start()
+m.model.sample_euler(zs, euler_time_grid(100)[:2], **kw)
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
