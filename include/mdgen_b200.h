@@ -177,12 +177,16 @@ int mdgen_abi_version(void);
 int64_t mdgen_launch_count(const mdgen_handle* h);
 /* Tuning / validation knobs (none of them is needed for normal use; the defaults are the measured-best path):
  *   "use_tc"        1 (default) tcgen05 tensor-core GEMMs and attention, 0 = exact-fp32 SIMT validation kernels
- *   "gemm_bf16"     1 (default) bf16 operands (kind::f16) for the token GEMMs, 0 = TF32 operands (kind::tf32)
+ *   "gemm_bf16"     operand type of the token GEMMs: 2 (default) fp16 (kind::f16), 1 = bf16 (kind::f16), 0 = TF32
+ *                   (kind::tf32). bf16 does not meet the 1e-3 parity tolerance on trained-like weights.
  *   "use_tc_attn"   1 (default) tcgen05 fused attention for sequences longer than 64
- *   "attn_variant"  build variant of that attention (default 3: bf16 P.V + staged pre-pass; bit 2 persistent
- *                   kernel, bit 3 with 12 softmax warps, bit 7 bound-adopted softmax reference; bits 4-6 are timing
- *                   aids whose output is undefined - see csrc/attention_tc.cuh)
- *   "l4_variant"    0 (default) shuffle-based S = 4 residue attention, 1 = shared-memory exchange kernel
+ *   "attn_variant"  build variant of that attention: 256 (default) generation 8 (csrc/attention_v8.cuh; +1 forces its
+ *                   2-query-tile kernel, +2 keeps every exponential on the MUFU pipe); 0-15 (+128) generation 7
+ *                   (csrc/attention_tc.cuh: bit 0 bf16 P.V, bit 1 staged pre-pass, bit 2 persistent kernel, bit 3 with
+ *                   12 softmax warps, bit 7 bound-adopted softmax reference; bits 4-6 are timing aids, output undefined)
+ *   "l4_variant"    1 (default) shared-memory exchange S = 4 residue attention, 0 = shuffle-based kernel
+ *   "fuse_resid_ln" 1: the out-proj / fc2 GEMMs store gate * branch and the next LayerNorm kernel adds it to the residual
+ *                   stream (measured neutral), 0 (default): residual add in the GEMM epilogue
  *   "tc_min_rows"   GEMMs with fewer rows (the IPA key-frame trunk) stay on the exact-fp32 skinny GEMM (1024)
  *   "use_graph", "graph_max_tokens"   CUDA-graph replay of the Euler steps for launch-bound workloads (1, 65536)
  *   "reuse_cond"    1: mdgen_forward keeps the conditioning embedding of its previous call (same cond object and
