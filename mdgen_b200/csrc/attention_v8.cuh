@@ -123,16 +123,26 @@ __global__ void __launch_bounds__(A8P_THREADS, 2) attn8_prep_kernel(AttnParams p
   const long long s = (blockIdx.x >> 1) / nkt;
   uint8_t* qimg0 = scratch + (size_t)sm.num_seq * kH * nkt * A8_IMG;
   const bool half_in = p.qkv_fmt != kFmtF32;
+  // token of key / query j of this sequence: seq_token is affine in j (one 64-bit division per block, not per row)
+  const long long tok_base = seq_token(sm, s, 0);
+  const long long tok_step = sm.elem_stride;
   if (half_in) {
-    const uint16_t* qkv = reinterpret_cast<const uint16_t*>(p.qkv);
+    const uint16_t* qkv = reinterpret_cast<const uint16_t*>(p.qkv) + hg * 192;
+    // 72 chunks of 16 bytes per row: q octet (24) | k octet (24) | v octet (24); a lane owns chunks lane, lane + 32, lane + 64
+    int soff[3];
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      const int ch = lane + 32 * u;
+      soff[u] = (ch / 24) * kC + (ch % 24) * 8;
+    }
     for (int row = warp; row < A8_KT; row += A8P_THREADS / 32) {
       const int j = kt * A8_KT + row;
       if (j < S) {
-        const long long tk = seq_token(sm, s, j);
-        const uint16_t* src = qkv + (size_t)tk * kQKV + hg * 192;
-        uint8_t* dst = a8p_smem + row * A8P_PITCH;
-        // 72 chunks: q octet (24) | k octet (24) | v octet (24)
-        for (int ch = lane; ch < 72; ch += 32) cp_async16(dst + ch * 16, src + (ch / 24) * kC + (ch % 24) * 8);
+        const uint16_t* src = qkv + (size_t)(tok_base + j * tok_step) * kQKV;
+        uint8_t* dst = a8p_smem + row * A8P_PITCH + lane * 16;
+        cp_async16(dst, src + soff[0]);
+        cp_async16(dst + 512, src + soff[1]);
+        if (lane < 8) cp_async16(dst + 1024, src + soff[2]);
       }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -147,7 +157,7 @@ __global__ void __launch_bounds__(A8P_THREADS, 2) attn8_prep_kernel(AttnParams p
   float k[kHD], v[kHD];
   float masked = 0.f;
   if (j < S) {
-    const long long tk = seq_token(sm, s, j);
+    const long long tk = tok_base + j * tok_step;
     float q[kHD];
     if (half_in) {
       const uint8_t* rowp = a8p_smem + r * A8P_PITCH + hl * 48;
