@@ -524,5 +524,16 @@ def test_rk_kernels_match_torch_and_residual_fusion_option():
     v0 = m.model.forward_inference(zs.cuda(), t, **kw)
     m.model.engine().set_option("fuse_resid_ln", 1)
     v1 = m.model.forward_inference(zs.cuda(), t, **kw)
-    assert max_rel(v1.cpu(), v0.cpu()) < 5e-4      # (one extra fp32 rounding per branch, amplified by the stress weights)
+    # one extra fp32 rounding per branch, amplified by the stress weights: both stay inside TOL of the golden velocity,
+    # so they are within 2*TOL of each other; on ordinary weights the two orders agree to fp32 round-off.
+    assert max_rel(v1.cpu(), gold["v"]) < TOL
+    assert max_rel(v1.cpu(), v0.cpu()) < 2 * TOL
+    case, args, cfg, sd, batch, zs, gold = load_case("sim_c1")
+    m = _wrapper(args, sd, "fp16")
+    kw = m.prep_batch(_dev(batch))["model_kwargs"]
+    t = torch.tensor(case["t_fwd"]).cuda()
+    v0 = m.model.forward_inference(zs.cuda(), t, **kw)
+    m.model.engine().set_option("fuse_resid_ln", 1)
+    v1 = m.model.forward_inference(zs.cuda(), t, **kw)
+    assert max_rel(v1.cpu(), v0.cpu()) < 2e-5
     assert max_rel(v1.cpu(), gold["v"]) < TOL
