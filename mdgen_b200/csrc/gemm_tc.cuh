@@ -373,6 +373,17 @@ __global__ void __launch_bounds__(128 + 32 * tc_epi_warps(MODE), 1) gemm_tc_kern
           }
         }
       }
+      // gate row of this warp's 32 token rows: one sample index per tile when the rows do not straddle a sample
+      // boundary (two integer divisions per tile instead of two per row and chunk; the per-row form was ~2/3 of
+      // the epilogue's instructions)
+      bool gate_uniform = false;
+      const float* gate_row0 = nullptr;
+      if (MODE == EPI_RESID_GATE || MODE == EPI_GATE) {
+        const long long mlast = (mbase + 31 < M ? mbase + 31 : M - 1);
+        const long long b_first = mbase / ep.mod.tokens_per_b;
+        gate_uniform = (mlast / ep.mod.tokens_per_b) == b_first;
+        gate_row0 = gate_base + (size_t)(((int)b_first % ep.mod.bmod) * ep.mod.bstride) * ep.mod.width;
+      }
       mbar_wait(tfull_bar(buf), bphase);
       tc_fence_after();
 #pragma unroll 1
@@ -401,6 +412,9 @@ __global__ void __launch_bounds__(128 + 32 * tc_epi_warps(MODE), 1) gemm_tc_kern
         const int n = n0 + c0 + 4 * c4;
         float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (ep.bias) bias4 = *reinterpret_cast<const float4*>(ep.bias + n);
+        float4 gate4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if ((MODE == EPI_RESID_GATE || MODE == EPI_GATE) && gate_uniform)
+          gate4 = *reinterpret_cast<const float4*>(gate_row0 + n);
         // 8 lanes cover one 128-byte row segment; a warp instruction covers 4 rows
 #pragma unroll
         for (int itr = 0; itr < 8; ++itr) {
@@ -411,15 +425,21 @@ __global__ void __launch_bounds__(128 + 32 * tc_epi_warps(MODE), 1) gemm_tc_kern
             a.x += bias4.x; a.y += bias4.y; a.z += bias4.z; a.w += bias4.w;
             if (MODE == EPI_GELU) { gelu_fast2(a.x, a.y); gelu_fast2(a.z, a.w); }
             if (MODE == EPI_RESID_GATE) {
-              const int bb = (int)(m / ep.mod.tokens_per_b) % ep.mod.bmod;
-              const float4 g = *reinterpret_cast<const float4*>(gate_base + (size_t)(bb * ep.mod.bstride) * ep.mod.width + n);
+              float4 g = gate4;
+              if (!gate_uniform) {
+                const int bb = (int)(m / ep.mod.tokens_per_b) % ep.mod.bmod;
+                g = *reinterpret_cast<const float4*>(gate_base + (size_t)(bb * ep.mod.bstride) * ep.mod.width + n);
+              }
               a.x = res[itr].x + g.x * a.x; a.y = res[itr].y + g.y * a.y;
               a.z = res[itr].z + g.z * a.z; a.w = res[itr].w + g.w * a.w;
             }
             if (MODE == EPI_RESID) { a.x += res[itr].x; a.y += res[itr].y; a.z += res[itr].z; a.w += res[itr].w; }
             if (MODE == EPI_GATE) {
-              const int bb = (int)(m / ep.mod.tokens_per_b) % ep.mod.bmod;
-              const float4 g = *reinterpret_cast<const float4*>(gate_base + (size_t)(bb * ep.mod.bstride) * ep.mod.width + n);
+              float4 g = gate4;
+              if (!gate_uniform) {
+                const int bb = (int)(m / ep.mod.tokens_per_b) % ep.mod.bmod;
+                g = *reinterpret_cast<const float4*>(gate_base + (size_t)(bb * ep.mod.bstride) * ep.mod.width + n);
+              }
               a.x *= g.x; a.y *= g.y; a.z *= g.z; a.w *= g.w;
             }
             if (ep.round_out) { a.x = round_operand(a.x, ep.round_out); a.y = round_operand(a.y, ep.round_out); a.z = round_operand(a.z, ep.round_out); a.w = round_operand(a.w, ep.round_out); }
