@@ -200,7 +200,9 @@ int64_t mdgen_get_option(const mdgen_handle* h, const char* key);
 int mdgen_profile_dump(mdgen_handle* h, char* buf, int64_t cap);
 
 /* Test hook: out[M,N] = act(A[M,K] · W[N,K]^T + bias) through one of the library's GEMM kernels
- * (use_tc = 1: tcgen05 TF32 kernel, operands are rounded to TF32 first; 0: fp32 SIMT kernel).
+ * (use_tc = 0: fp32 SIMT kernel; 1: tcgen05 kernel, operands rounded to TF32 first; 2 / 3: bf16 / fp16 operands, fp32 output;
+ * 4 / 5: bf16 / fp16 operands and 16-bit output -- the form of the QKV / fc1 GEMMs, bulk-tensor-store epilogue --
+ * widened to fp32 into `out`).
  * act: 0 = none, 1 = erf-GELU. Lets the parity tests A/B the tensor-core kernel in isolation. */
 int mdgen_debug_linear(mdgen_handle* h, const float* A, const float* W, const float* bias, int64_t M,
                        int32_t N, int32_t K, int32_t act, int32_t use_tc, float* out, void* stream);

@@ -381,6 +381,13 @@ __global__ void to_f16_kernel(const float* __restrict__ src, uint16_t* __restric
   dst[i] = (uint16_t)(pack_f16x2_rn(src[i], 0.f) & 0xFFFFu);
 }
 
+// 16-bit (bf16 / fp16 per `fmt`) -> fp32 widening copy (debug entry point: 16-bit GEMM outputs handed back as fp32)
+__global__ void from_half_kernel(const uint16_t* __restrict__ src, float* __restrict__ dst, long long n, int fmt) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  dst[i] = unpack_half2((uint32_t)src[i], fmt).x;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Training / validation loss pieces (mdgen/transport/transport.py:138-223)
 // Interpolant plan (mdgen/transport/path.py:118-135): xt = alpha(t) x1 + sigma(t) x0, ut = alpha'(t) x1 + sigma'(t) x0

@@ -20,8 +20,10 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <mutex>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -246,10 +248,17 @@ __device__ __forceinline__ void tc_epilogue4(const Epilogue& ep, const float* ga
 //          same descriptors and 32-byte K advance, twice the MMA rate and half the shared-memory/L2
 //          operand traffic per FLOP (which is what bounds the fp32-operand variant).
 // BF16OUT: the epilogue stores the same 16-bit format (q|k|v, the fc1 hidden activations).
-template <int MODE, bool BF16IN, bool BF16OUT>
+// TMAOUT:  (16-bit outputs, store / GELU epilogues) thread = accumulator row: bias / GELU / pack on the registers that
+//          tcgen05.ld delivers, rows written into a 128-byte-swizzled 32 x 64 staging tile per warp and sent to global
+//          memory by ONE bulk-tensor (TMA) store per warp and tile. No per-row address arithmetic, bounds predicates,
+//          shared-memory read-back or st.global in the warps (12 -> ~2 instructions per output element); rows >= M are
+//          clipped by the tensor map.
+template <int MODE, bool BF16IN, bool BF16OUT, bool TMAOUT = false>
 __global__ void __launch_bounds__(128 + 32 * tc_epi_warps(MODE), 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                         const __grid_constant__ CUtensorMap tmB, long long M,
+                                                         const __grid_constant__ CUtensorMap tmB,
+                                                         const __grid_constant__ CUtensorMap tmO, long long M,
                                                          int N, int K, Epilogue ep) {
+  static_assert(!TMAOUT || (BF16OUT && (MODE == EPI_STORE || MODE == EPI_GELU)), "TMA-store epilogue: 16-bit store / GELU");
   constexpr int BKE = BF16IN ? 64 : 32;                   // elements per 128-byte K-block row
   constexpr int NEPI = tc_epi_warps(MODE);                // epilogue warps
   constexpr int ECOLS = TC_BN / (NEPI / 4);               // columns of the tile owned by one epilogue warp
@@ -342,6 +351,64 @@ __global__ void __launch_bounds__(128 + 32 * tc_epi_warps(MODE), 1) gemm_tc_kern
         tc_commit(tfull_bar(buf));                          // accumulator complete -> epilogue
       }
     }
+  } else if (warp >= 4 && TMAOUT) {
+    // ===================== epilogue warps, TMA-store form (TMEM -> regs -> swizzled smem tile -> bulk store) ==========
+    static_assert(!TMAOUT || ECOLS == 64, "one 64-column (128-byte) box per warp");
+    const int q = warp & 3;                                 // TMEM lane quarter of this warp
+    const int slice = (warp - 4) >> 2;                      // which 64-column slice of the tile
+    const uint32_t stg = sbase + TC_STAGES * TC_STAGE_BYTES + 1024 + (warp - 4) * 4096;   // 32 rows x 128 B, 1 KB aligned
+    const uint32_t row_addr = stg + lane * 128;
+    const uint32_t sw = (uint32_t)(lane & 7);
+    const bool f16 = ep.half_fmt == kFmtF16;
+    uint32_t it = 0;
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+      const uint32_t buf = it & 1u, bphase = (it >> 1) & 1u;
+      const int m0 = (int)(tile / n_blocks) * TC_BM + q * 32;
+      const int n0 = (int)(tile % n_blocks) * TC_BN + slice * 64;
+      mbar_wait(tfull_bar(buf), bphase);
+      tc_fence_after();
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // last tile's store has read the staging tile
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        float4 b4[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          b4[j] = ep.bias ? *reinterpret_cast<const float4*>(ep.bias + n0 + c * 32 + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        uint32_t v[32];
+        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * TC_BN + slice * 64 + c * 32, v);
+        tc_ld_wait();
+        if (c == 1) {                                       // accumulator is in registers: hand the buffer back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(buf));
+        }
+        auto finish = [&](auto is_f16) {                    // bias (+ GELU) + pack, 16-bit format fixed at compile time
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float a0 = __uint_as_float(v[4 * j]) + b4[j].x, a1 = __uint_as_float(v[4 * j + 1]) + b4[j].y;
+            float a2 = __uint_as_float(v[4 * j + 2]) + b4[j].z, a3 = __uint_as_float(v[4 * j + 3]) + b4[j].w;
+            if (MODE == EPI_GELU) { gelu_fast2(a0, a1); gelu_fast2(a2, a3); }
+            if (decltype(is_f16)::value) { v[2 * j] = pack_f16x2_rn(a0, a1); v[2 * j + 1] = pack_f16x2_rn(a2, a3); }
+            else { v[2 * j] = pack_bf16x2(a0, a1); v[2 * j + 1] = pack_bf16x2(a2, a3); }
+          }
+        };
+        if (f16) finish(std::true_type{}); else finish(std::false_type{});
+        // this row's 64 bytes of the chunk = 16-byte units 4c .. 4c+3 of the 128-byte row, XOR-swizzled by (row & 7)
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_addr + ((((uint32_t)(4 * c + u)) ^ sw) << 4)),
+                       "r"(v[4 * u]), "r"(v[4 * u + 1]), "r"(v[4 * u + 2]), "r"(v[4 * u + 3]) : "memory");
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                     ::"l"(reinterpret_cast<uint64_t>(&tmO)), "r"(n0), "r"(m0), "r"(stg) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   } else if (warp >= 4) {
     // ===================== epilogue warps (TMEM -> regs -> smem transpose -> global) =====================
     const int q = warp & 3;                                 // TMEM lane quarter of this warp
@@ -482,6 +549,11 @@ inline int device_sm_count() {
   if (!n[d]) cudaDeviceGetAttribute(&n[d], cudaDevAttrMultiProcessorCount, d);
   return n[d];
 }
+// debugging / A-B switch: MDGEN_NO_TMA_OUT=1 keeps the 16-bit-output GEMMs on the shared-memory-transpose epilogue
+inline bool tc_no_tma_out() {
+  static const bool v = [] { const char* e = getenv("MDGEN_NO_TMA_OUT"); return e && e[0] == '1'; }();
+  return v;
+}
 inline bool tc_gemm_supported(int N, int K, bool bf16 = false) {
   const int bk = bf16 ? 64 : TC_BK;
   return (N % TC_BN == 0) && (K % bk == 0) && K >= bk;
@@ -550,13 +622,14 @@ inline int get_tmap(const void* ptr, long long rows, int cols, int ld, int box_r
   return 0;
 }
 
-template <int MODE, bool BF16IN, bool BF16OUT>
+template <int MODE, bool BF16IN, bool BF16OUT, bool TMAOUT = false>
 inline int tc_launch_mode(const CUtensorMap& ta, const CUtensorMap& tb, long long M, int N, int K,
-                          const Epilogue& ep, cudaStream_t s, int grid, std::string* err) {
+                          const Epilogue& ep, cudaStream_t s, int grid, std::string* err,
+                          const CUtensorMap* to = nullptr) {
   static bool configured[kMaxDevices] = {false};
   const int dev = current_device();
   if (!configured[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<MODE, BF16IN, BF16OUT>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<MODE, BF16IN, BF16OUT, TMAOUT>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
     if (e != cudaSuccess) {
       if (err) *err = std::string("cudaFuncSetAttribute(gemm_tc): ") + cudaGetErrorString(e);
@@ -564,7 +637,8 @@ inline int tc_launch_mode(const CUtensorMap& ta, const CUtensorMap& tb, long lon
     }
     configured[dev] = true;
   }
-  gemm_tc_kernel<MODE, BF16IN, BF16OUT><<<grid, 128 + 32 * tc_epi_warps(MODE), TC_SMEM_BYTES, s>>>(ta, tb, M, N, K, ep);
+  gemm_tc_kernel<MODE, BF16IN, BF16OUT, TMAOUT><<<grid, 128 + 32 * tc_epi_warps(MODE), TC_SMEM_BYTES, s>>>(
+      ta, tb, to ? *to : ta, M, N, K, ep);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     if (err) *err = std::string("gemm_tc launch: ") + cudaGetErrorString(e);
@@ -600,6 +674,17 @@ inline int tc_gemm_launch(int mode, const void* A, int lda, const void* W, int l
       case EPI_GATE: return tc_launch_mode<EPI_GATE, true, false>(ta, tb, M, N, K, ep, s, grid, err);
     }
   } else {
+    // 16-bit output: bulk-tensor stores when the output rows satisfy TMA's 16-byte address / stride rules
+    const bool tma_out = !tc_no_tma_out() && ep.ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(ep.out) & 15) == 0 &&
+                         ep.round_out == 0 && M < (1ll << 31);
+    if (tma_out) {
+      CUtensorMap to;
+      if (get_tmap(ep.out, M, N, ep.ldo, 32, true, &to, err)) return -2;
+      switch (mode) {
+        case EPI_STORE: return tc_launch_mode<EPI_STORE, true, true, true>(ta, tb, M, N, K, ep, s, grid, err, &to);
+        case EPI_GELU: return tc_launch_mode<EPI_GELU, true, true, true>(ta, tb, M, N, K, ep, s, grid, err, &to);
+      }
+    }
     switch (mode) {
       case EPI_STORE: return tc_launch_mode<EPI_STORE, true, true>(ta, tb, M, N, K, ep, s, grid, err);
       case EPI_GELU: return tc_launch_mode<EPI_GELU, true, true>(ta, tb, M, N, K, ep, s, grid, err);

@@ -1129,8 +1129,14 @@ int mdgen_debug_linear(mdgen_handle* h, const float* A, const float* W, const fl
   int mode = act ? EPI_GELU : EPI_STORE;
   if (use_tc) {
 #ifndef MDGEN_NO_TC
-    const bool bf = use_tc >= 2;          // 3: fp16 operands, 2: bf16 operands (kind::f16), 1: TF32 operands
+    // 1: TF32 operands; 2 / 3: bf16 / fp16 operands, fp32 output; 4 / 5: bf16 / fp16 operands AND output (the QKV / fc1
+    // form, bulk-tensor-store epilogue), widened to fp32 into `out` afterwards
+    const bool out16 = use_tc >= 4;
+    if (out16) use_tc -= 2;
+    const bool bf = use_tc >= 2;
     ep.half_fmt = use_tc == 3 ? kFmtF16 : kFmtBF16;
+    uint16_t* out_h = nullptr;
+    if (out16) { TRY(dev_alloc_t(h, &out_h, (size_t)M * N)); ep.out = reinterpret_cast<float*>(out_h); }
     if (!tc_gemm_supported(N, K, bf)) { h->err = "shape unsupported by the tensor-core GEMM"; return MDGEN_E_INVALID; }
     float *Ar = nullptr, *Wr = nullptr;   // rounded operand copies (fp32 containers or bf16 arrays)
     TRY(dev_alloc_t(h, &Ar, (size_t)M * K));
@@ -1145,10 +1151,13 @@ int mdgen_debug_linear(mdgen_handle* h, const float* A, const float* W, const fl
       pack_rows_kernel<<<(unsigned)(((size_t)M * K + 255) / 256), 256, 0, s>>>(A, Ar, M, K, K, 0, 1.f, 1);
       pack_rows_kernel<<<(unsigned)(((size_t)N * K + 255) / 256), 256, 0, s>>>(W, Wr, N, K, K, 0, 1.f, 1);
     }
-    int rc = tc_gemm_launch(mode, Ar, K, Wr, K, M, N, K, ep, s, &h->err, bf, false);
+    int rc = tc_gemm_launch(mode, Ar, K, Wr, K, M, N, K, ep, s, &h->err, bf, out16);
+    if (out16 && rc == 0)
+      from_half_kernel<<<(unsigned)(((size_t)M * N + 255) / 256), 256, 0, s>>>(out_h, out, (long long)M * N, ep.half_fmt);
     cudaStreamSynchronize(s);
     dev_free(h, Ar);
     dev_free(h, Wr);
+    if (out_h) dev_free(h, out_h);
     return rc == 0 ? MDGEN_OK : MDGEN_E_CUDA;
 #else
     h->err = "library built without tensor-core kernels";

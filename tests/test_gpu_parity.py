@@ -267,6 +267,33 @@ def test_tc_gemm_matches_fp64_of_rounded_operands(shape, act, dtype):
     assert float((y.double() - ref32).abs().max() / ref32.abs().max()) < (2e-3 if dtype == "tf32" else 2e-2)
 
 
+@pytest.mark.parametrize("shape", [(128, 192, 64), (1000, 1152, 384), (50000, 1536, 384), (333, 384, 384), (31, 192, 128)])
+@pytest.mark.parametrize("fmt", ["bf16", "f16"])
+@pytest.mark.parametrize("act", [0, 1])
+def test_tc_gemm_16bit_output_epilogue(shape, act, fmt):
+    """The QKV / fc1 form of the tcgen05 GEMM (16-bit operands AND 16-bit output, written by bulk-tensor stores from a
+    swizzled staging tile, rows >= M clipped by the tensor map): every output is the correctly-rounded-to-16-bit value of
+    the fp64 product of the rounded operands up to fp32 accumulation noise, including ragged M."""
+    from mdgen_b200._lib import Engine
+    from mdgen_b200.config import config_from_args, default_args
+    eng = Engine(config_from_args(default_args(sim_condition=True, prepend_ipa=True, abs_pos_emb=True, crop=4)))
+    M, N, K = shape
+    g = torch.Generator(device="cuda").manual_seed(M + N + K + 1)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    W = torch.randn(N, K, device="cuda", generator=g) / K ** 0.5
+    b = torch.randn(N, device="cuda", generator=g)
+    rnd = _bf16 if fmt == "bf16" else (lambda x: x.half().float())
+    y = eng.debug_linear(A, W, b, act=act, use_tc=4 if fmt == "bf16" else 5)
+    ref = rnd(A).double() @ rnd(W).double().T + b.double()
+    if act:
+        ref = torch.nn.functional.gelu(ref)
+    ulp = 2.0 ** -8 if fmt == "bf16" else 2.0 ** -11
+    err = (y.double() - ref).abs()
+    bound = ref.abs() * ulp * 1.02 + 2e-5 * float(ref.abs().max())
+    assert bool((err <= bound).all()), float((err - bound).max())
+    assert torch.equal(y, rnd(y))                         # values are representable in the 16-bit format
+
+
 # ---------------------------------------------------------------------------------------------
 # Size-independent properties at BASELINE.json's full sequence shape (T = 1000 frames, crop 4),
 # where the CPU oracle is too slow to be the checker.
