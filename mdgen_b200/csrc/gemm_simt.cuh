@@ -25,6 +25,8 @@ struct Epilogue {
   int ldo;
   int round_out;       // round result to TF32 (output only feeds another tensor-core GEMM)
   int half_fmt;        // tensor-core kernel with 16-bit operands / output: kFmtBF16 or kFmtF16
+  int dbg;             // measurement switches of the tensor-core kernel (results are garbage): bit 0 = no TMA operand
+                       // loads (MMA-issue-bound rate), bit 1 = no MMAs (operand-fill-bound rate)
 };
 
 template <int MODE>

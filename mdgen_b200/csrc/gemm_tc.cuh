@@ -169,8 +169,7 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return 0.5f * x * (1.0f + erf_v);
 }
 
-// The same erf-GELU for two values at once with Blackwell's packed fp32x2 arithmetic (one issue slot per pair for
-// every multiply / FMA; the fc1 epilogue is issue bound): identical operations and rounding as gelu_fast per element.
+// Packed fp32x2 helpers (Blackwell: one issue slot per pair for every add / multiply / FMA).
 __device__ __forceinline__ uint64_t pk2(float a, float b) {
   uint64_t r;
   asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
@@ -188,35 +187,29 @@ __device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
   return r;
 }
 __host__ __device__ constexpr uint64_t splat2(uint32_t bits) { return ((uint64_t)bits << 32) | bits; }
+// gelu(x) = max(x, 0) - |x|/2 * erfc(|x| / sqrt 2), with erfc(z) = 2^(z * P(z)) on z in [0, 4] (clamped: erfc(4) = 1.5e-8):
+// P = degree-6 weighted-minimax fit of log2(erfc(z)) / z (tools/fit_erfc_poly.py; |gelu error| <= 4e-7 absolute, the same class
+// as the Abramowitz-Stegun form above) -> ONE MUFU (ex2) per element instead of two (rcp + ex2): the fc1 epilogue sits on the
+// MUFU pipe (16 / clk / SM; 393 M outputs per launch), everything else is packed fp32x2 arithmetic.
 __device__ __forceinline__ void gelu_fast2(float& x0, float& x1) {
-  constexpr uint64_t kOne = splat2(0x3F800000u), kP = splat2(0x3EA7BA05u) /*0.3275911*/,
-                     kA5 = splat2(0x3F87DC22u) /*1.061405429*/, kA4 = splat2(0xBFBA00E3u) /*-1.453152027*/,
-                     kA3 = splat2(0x3FB5F0E3u) /*1.421413741*/, kA2 = splat2(0xBE91A98Eu) /*-0.284496736*/,
-                     kA1 = splat2(0x3E827906u) /*0.254829592*/, kNegL2e = splat2(0xBFB8AA3Bu) /*-1.4426950408889634*/,
-                     kHalf = splat2(0x3F000000u);
-  const float z0 = fabsf(x0) * 0.70710678118654752440f, z1 = fabsf(x1) * 0.70710678118654752440f;
+  constexpr uint64_t kC0 = splat2(0xBFD05F7Au) /*-1.6279137*/, kC1 = splat2(0xBF6B1796u) /*-0.91832864*/,
+                     kC2 = splat2(0xBE1889EEu) /*-0.14896366*/, kC3 = splat2(0x3CF14663u) /*0.029452508*/,
+                     kC4 = splat2(0xBB16E11Bu) /*-0.0023022357*/, kC5 = splat2(0xB9F1FF41u) /*-0.00046157281*/,
+                     kC6 = splat2(0x38D22DABu) /*0.00010022087*/, kNegRsqrt2 = splat2(0xBF3504F3u) /*-0.70710678*/;
+  const float z0 = fminf(fabsf(x0) * 0.70710678118654752440f, 4.0f), z1 = fminf(fabsf(x1) * 0.70710678118654752440f, 4.0f);
   const uint64_t z = pk2(z0, z1);
-  float d0, d1;
-  upk2(fma2(kP, z, kOne), d0, d1);
-  float t0, t1;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
-  const uint64_t t = pk2(t0, t1);
-  uint64_t poly = fma2(kA5, t, kA4);
-  poly = fma2(poly, t, kA3);
-  poly = fma2(poly, t, kA2);
-  poly = fma2(poly, t, kA1);
-  poly = mul2(poly, t);
-  float a0, a1;
-  upk2(mul2(mul2(z, z), kNegL2e), a0, a1);           // (-z) * z * log2(e) == -(z * z) * log2(e) up to the sign bit
+  uint64_t p = fma2(kC6, z, kC5);
+  p = fma2(p, z, kC4);
+  p = fma2(p, z, kC3);
+  p = fma2(p, z, kC2);
+  p = fma2(p, z, kC1);
+  p = fma2(p, z, kC0);
+  float q0, q1;
+  upk2(mul2(p, z), q0, q1);
   float e0, e1;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
-  float p0, p1;
-  upk2(poly, p0, p1);
-  const float erf0 = copysignf(fmaf(-p0, e0, 1.0f), x0), erf1 = copysignf(fmaf(-p1, e1, 1.0f), x1);
-  const uint64_t hx = mul2(kHalf, pk2(x0, x1));
-  upk2(fma2(hx, pk2(erf0, erf1), hx), x0, x1);       // 0.5 x (1 + erf)
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(q0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(q1));
+  upk2(fma2(mul2(z, kNegRsqrt2), pk2(e0, e1), pk2(fmaxf(x0, 0.f), fmaxf(x1, 0.f))), x0, x1);
 }
 
 // ---- vectorised epilogue on 4 consecutive columns ------------------------------------------------
@@ -308,10 +301,14 @@ __global__ void __launch_bounds__(128 + 32 * tc_epi_warps(MODE), 1) gemm_tc_kern
         const int n0 = (int)(tile % n_blocks) * TC_BN;
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_expect_tx(full_bar(stage), TC_STAGE_BYTES);
-          const uint32_t sa = sbase + stage * TC_STAGE_BYTES;
-          tma_load_2d(sa, &tmA, full_bar(stage), kb * BKE, m0);
-          tma_load_2d(sa + TC_A_BYTES, &tmB, full_bar(stage), kb * BKE, n0);
+          if (ep.dbg & 1) {
+            mbar_arrive(full_bar(stage));
+          } else {
+            mbar_expect_tx(full_bar(stage), TC_STAGE_BYTES);
+            const uint32_t sa = sbase + stage * TC_STAGE_BYTES;
+            tma_load_2d(sa, &tmA, full_bar(stage), kb * BKE, m0);
+            tma_load_2d(sa + TC_A_BYTES, &tmB, full_bar(stage), kb * BKE, n0);
+          }
           if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -337,6 +334,7 @@ __global__ void __launch_bounds__(128 + 32 * tc_epi_warps(MODE), 1) gemm_tc_kern
           const uint64_t bdesc = umma_desc_k128(sa + TC_A_BYTES);
 #pragma unroll
           for (int k = 0; k < TC_BK / 8; ++k) {
+            if (ep.dbg & 2) break;
             // advance 8 tf32 = 32 bytes along K inside the 128-byte swizzle row: +2 in 16-B units
             if (BF16IN)
               tc_mma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
@@ -534,6 +532,194 @@ __global__ void __launch_bounds__(128 + 32 * tc_epi_warps(MODE), 1) gemm_tc_kern
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Weight-stationary form of the 16-bit GEMM for K <= 384 (QKV, fc1: M = all tokens, K = 384).
+// Measured on the kernel above with its operand loads / MMAs switched off (Epilogue::dbg): QKV runs 0.171 ms with MMAs
+// only, 0.197 ms with operand fills only and 0.255 ms with both -- each 128 x 192 tile pulls 98 KB of A AND 147 KB of W
+// from L2 for 18.9 MFLOP. Here a CTA owns ONE 192-row block of W for its whole life (147 KB resident in shared memory,
+// loaded once) and walks down the token rows of that column block, so a tile costs 98 KB of operand fill instead of 245.
+//   warp 0: TMA producer (W block once, then a 3-stage ring of 128 x 64 A blocks)   warp 1: MMA issuer
+//   warp 2: TMEM allocator        warps 4-15: epilogue, bulk-tensor stores of 32 x 32 chunks (2 KB staging per warp)
+// Measured (profiles/r2_gemm_epilogue.md): the ring's depth IN TIME is what bounds these K = 384 GEMMs, not bytes: QKV takes
+// 0.51 / 0.33 / 0.24 ms with a 1 / 2 / 3-deep A ring (round trip MMA retire -> refill -> data landed ~0.7 us against 0.23 us
+// of MMA work per K-block), an L2 prefetch of A ahead of the loads and a single load+MMA thread were both slower.
+// CTA c works on column block c % n_blocks; the CTAs of one column block interleave its row tiles, so the CTAs that read
+// the same A tile do so at about the same time (one DRAM read, the other column blocks hit L2).
+constexpr int WS_MAXKB = 6;                                  // K <= 6 x 64
+constexpr int WS_ASTAGES = 3;
+constexpr int WS_A_BYTES = TC_BM * 128;                      // 16 KB: 128 rows x 64 16-bit elements
+constexpr int WS_B_BYTES = TC_BN * 128;                      // 24 KB per K-block of the resident W block
+constexpr int WS_STG_BYTES = 12 * 2048;                      // 32 rows x 64 B per epilogue warp
+constexpr int WS_SMEM_BYTES = WS_MAXKB * WS_B_BYTES + WS_ASTAGES * WS_A_BYTES + 1024 /*barriers*/ + WS_STG_BYTES + 1024 /*align*/;
+
+template <int MODE>
+__global__ void __launch_bounds__(512, 1) gemm_tc_ws_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                            const __grid_constant__ CUtensorMap tmB,
+                                                            const __grid_constant__ CUtensorMap tmO, long long M, int N,
+                                                            int K, Epilogue ep) {
+  static_assert(MODE == EPI_STORE || MODE == EPI_GELU, "weight-stationary GEMM: 16-bit store / GELU epilogues");
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sB = sbase;                                               // [kblocks][192 rows][128 B] swizzle-128B
+  const uint32_t sA = sbase + WS_MAXKB * WS_B_BYTES;                       // [stage][128 rows][128 B]
+  const uint32_t bar_base = sA + WS_ASTAGES * WS_A_BYTES;
+  auto full_bar = [&](int st) { return bar_base + 8u * st; };
+  auto empty_bar = [&](int st) { return bar_base + 8u * (WS_ASTAGES + st); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * WS_ASTAGES + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * WS_ASTAGES + 2 + b); };
+  const uint32_t bfull_bar = bar_base + 8u * (2 * WS_ASTAGES + 4);
+  const uint32_t tmem_slot_addr = bar_base + 8u * (2 * WS_ASTAGES + 5);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot_addr - smem_u32(smem_raw)));
+  const uint32_t stg_base = bar_base + 1024;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_blocks = N / TC_BN;
+  const long long m_blocks = (M + TC_BM - 1) / TC_BM;
+  const int kblocks = K / 64;
+  const int nb = (int)(blockIdx.x % n_blocks);                             // this CTA's column block of W
+  const int rank = (int)(blockIdx.x / n_blocks);                           // its rank among the CTAs of that block
+  const int group = (int)(gridDim.x / n_blocks) + (nb < (int)(gridDim.x % n_blocks) ? 1 : 0);
+  const int n0 = nb * TC_BN;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmO)) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int st = 0; st < WS_ASTAGES; ++st) { mbar_init(full_bar(st), 1); mbar_init(empty_bar(st), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 12); }
+    mbar_init(bfull_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(tmem_slot_addr), "r"((uint32_t)TC_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      if (!(ep.dbg & 1)) {
+        mbar_expect_tx(bfull_bar, (uint32_t)kblocks * WS_B_BYTES);
+        for (int kb = 0; kb < kblocks; ++kb) tma_load_2d(sB + kb * WS_B_BYTES, &tmB, bfull_bar, kb * 64, n0);
+      } else {
+        mbar_arrive(bfull_bar);
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long mt = rank; mt < m_blocks; mt += group) {
+        const int m0 = (int)mt * TC_BM;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          if (ep.dbg & 1) {
+            mbar_arrive(full_bar(stage));
+          } else {
+            mbar_expect_tx(full_bar(stage), WS_A_BYTES);
+            tma_load_2d(sA + stage * WS_A_BYTES, &tmA, full_bar(stage), kb * 64, m0);
+          }
+          if (++stage == WS_ASTAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer (one thread) =====================
+      const uint32_t idesc = ep.half_fmt == kFmtF16 ? umma_idesc_f16(TC_BM, TC_BN) : umma_idesc_bf16(TC_BM, TC_BN);
+      mbar_wait(bfull_bar, 0);
+      tc_fence_after();
+      int stage = 0;
+      uint32_t phase = 0, it = 0;
+      for (long long mt = rank; mt < m_blocks; mt += group, ++it) {
+        const uint32_t buf = it & 1u, bphase = (it >> 1) & 1u;
+        mbar_wait(tempty_bar(buf), bphase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + buf * TC_BN;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint64_t adesc = umma_desc_k128(sA + stage * WS_A_BYTES);
+          const uint64_t bdesc = umma_desc_k128(sB + kb * WS_B_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (ep.dbg & 2) break;
+            tc_mma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+          }
+          tc_commit(empty_bar(stage));
+          if (++stage == WS_ASTAGES) { stage = 0; phase ^= 1u; }
+        }
+        tc_commit(tfull_bar(buf));
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue warps (TMEM -> regs -> swizzled 32 x 32 chunk -> bulk-tensor store) ==========
+    const int q = warp & 3;
+    const int slice = (warp - 4) >> 2;
+    const uint32_t stg = stg_base + (warp - 4) * 2048;                     // 32 rows x 64 B, swizzle-64B
+    const uint32_t row_addr = stg + lane * 64;
+    const uint32_t sw = (uint32_t)((lane >> 1) & 3);
+    const bool f16 = ep.half_fmt == kFmtF16;
+    uint32_t it = 0;
+    for (long long mt = rank; mt < m_blocks; mt += group, ++it) {
+      const uint32_t buf = it & 1u, bphase = (it >> 1) & 1u;
+      const int m0 = (int)mt * TC_BM + q * 32;
+      const int nc = n0 + slice * 64;
+      mbar_wait(tfull_bar(buf), bphase);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        float4 b4[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          b4[j] = ep.bias ? *reinterpret_cast<const float4*>(ep.bias + nc + c * 32 + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        uint32_t v[32];
+        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * TC_BN + slice * 64 + c * 32, v);
+        tc_ld_wait();
+        if (c == 1) {                                       // accumulator is in registers: hand the buffer back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(buf));
+        }
+        auto finish = [&](auto is_f16) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float a0 = __uint_as_float(v[4 * j]) + b4[j].x, a1 = __uint_as_float(v[4 * j + 1]) + b4[j].y;
+            float a2 = __uint_as_float(v[4 * j + 2]) + b4[j].z, a3 = __uint_as_float(v[4 * j + 3]) + b4[j].w;
+            if (MODE == EPI_GELU) { gelu_fast2(a0, a1); gelu_fast2(a2, a3); }
+            if (decltype(is_f16)::value) { v[2 * j] = pack_f16x2_rn(a0, a1); v[2 * j + 1] = pack_f16x2_rn(a2, a3); }
+            else { v[2 * j] = pack_bf16x2(a0, a1); v[2 * j + 1] = pack_bf16x2(a2, a3); }
+          }
+        };
+        if (f16) finish(std::true_type{}); else finish(std::false_type{});
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous chunk's store has read the staging tile
+        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_addr + ((((uint32_t)u) ^ sw) << 4)),
+                       "r"(v[4 * u]), "r"(v[4 * u + 1]), "r"(v[4 * u + 2]), "r"(v[4 * u + 3]) : "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                       ::"l"(reinterpret_cast<uint64_t>(&tmO)), "r"(nc + c * 32), "r"(m0), "r"(stg) : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TC_TMEM_COLS) : "memory");
+  }
+}
+
 // ---- host side -------------------------------------------------------------------------------
 // Launch attributes (cudaFuncSetAttribute) and the SM count are per device: a process may own
 // handles on several GPUs, so the "already configured" state is kept per device ordinal.
@@ -552,6 +738,11 @@ inline int device_sm_count() {
 // debugging / A-B switch: MDGEN_NO_TMA_OUT=1 keeps the 16-bit-output GEMMs on the shared-memory-transpose epilogue
 inline bool tc_no_tma_out() {
   static const bool v = [] { const char* e = getenv("MDGEN_NO_TMA_OUT"); return e && e[0] == '1'; }();
+  return v;
+}
+// MDGEN_NO_WS=1 keeps the K <= 384 GEMMs on the tile-streaming kernel
+inline bool tc_no_ws() {
+  static const bool v = [] { const char* e = getenv("MDGEN_NO_WS"); return e && e[0] == '1'; }();
   return v;
 }
 inline bool tc_gemm_supported(int N, int K, bool bf16 = false) {
@@ -578,17 +769,21 @@ inline PFN_encodeTiled get_encode_fn(std::string* err) {
 }
 
 // 2-D fp32 row-major [rows, cols] (leading dimension ld elements), box = [box_rows, 32 cols], SWIZZLE_128B
+// (box_cols = 32 with 16-bit elements: 64-byte rows, SWIZZLE_64B -- the store chunks of the weight-stationary kernel)
 inline int make_tmap_2d(CUtensorMap* map, const void* ptr, long long rows, int cols, int ld, int box_rows,
-                        bool bf16, std::string* err) {
+                        bool bf16, std::string* err, int box_cols = 0) {
   PFN_encodeTiled fn = get_encode_fn(err);
   if (!fn) return -2;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * (bf16 ? 2 : 4)};
-  cuuint32_t box[2] = {(cuuint32_t)(bf16 ? 64 : TC_BK), (cuuint32_t)box_rows};   // 128-byte rows either way
+  if (!box_cols) box_cols = bf16 ? 64 : TC_BK;                                   // 128-byte rows either way
+  const bool sw64 = box_cols * (bf16 ? 2 : 4) == 64;
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                   const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     if (err) *err = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r);
@@ -598,23 +793,23 @@ inline int make_tmap_2d(CUtensorMap* map, const void* ptr, long long rows, int c
 }
 
 struct TmapCacheEntry {
-  const void* ptr; long long rows; int cols, ld, box_rows; bool bf16;
+  const void* ptr; long long rows; int cols, ld, box_rows; bool bf16; int box_cols;
   CUtensorMap map;
 };
 
 inline int get_tmap(const void* ptr, long long rows, int cols, int ld, int box_rows, bool bf16, CUtensorMap* out,
-                    std::string* err) {
+                    std::string* err, int box_cols = 0) {
   static std::vector<TmapCacheEntry> cache;
   static std::mutex mu;                      // handles on different host threads share this cache
   std::lock_guard<std::mutex> lock(mu);
   for (auto& e : cache)
     if (e.ptr == ptr && e.rows == rows && e.cols == cols && e.ld == ld && e.box_rows == box_rows &&
-        e.bf16 == bf16) {
+        e.bf16 == bf16 && e.box_cols == box_cols) {
       *out = e.map;
       return 0;
     }
-  TmapCacheEntry e{ptr, rows, cols, ld, box_rows, bf16, {}};
-  int rc = make_tmap_2d(&e.map, ptr, rows, cols, ld, box_rows, bf16, err);
+  TmapCacheEntry e{ptr, rows, cols, ld, box_rows, bf16, box_cols, {}};
+  int rc = make_tmap_2d(&e.map, ptr, rows, cols, ld, box_rows, bf16, err, box_cols);
   if (rc) return rc;
   if (cache.size() > 4096) cache.clear();
   cache.push_back(e);
@@ -642,6 +837,28 @@ inline int tc_launch_mode(const CUtensorMap& ta, const CUtensorMap& tb, long lon
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     if (err) *err = std::string("gemm_tc launch: ") + cudaGetErrorString(e);
+    return -2;
+  }
+  return 0;
+}
+
+template <int MODE>
+inline int tc_launch_ws(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, long long M, int N, int K,
+                        const Epilogue& ep, cudaStream_t s, int grid, std::string* err) {
+  static bool configured[kMaxDevices] = {false};
+  const int dev = current_device();
+  if (!configured[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_ws_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_BYTES);
+    if (e != cudaSuccess) {
+      if (err) *err = std::string("cudaFuncSetAttribute(gemm_tc_ws): ") + cudaGetErrorString(e);
+      return -2;
+    }
+    configured[dev] = true;
+  }
+  gemm_tc_ws_kernel<MODE><<<grid, 512, WS_SMEM_BYTES, s>>>(ta, tb, to, M, N, K, ep);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    if (err) *err = std::string("gemm_tc_ws launch: ") + cudaGetErrorString(e);
     return -2;
   }
   return 0;
@@ -677,6 +894,12 @@ inline int tc_gemm_launch(int mode, const void* A, int lda, const void* W, int l
     // 16-bit output: bulk-tensor stores when the output rows satisfy TMA's 16-byte address / stride rules
     const bool tma_out = !tc_no_tma_out() && ep.ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(ep.out) & 15) == 0 &&
                          ep.round_out == 0 && M < (1ll << 31);
+    if (tma_out && !tc_no_ws() && K <= WS_MAXKB * 64 && tiles >= 4ll * num_sms && N / TC_BN <= grid && (mode == EPI_STORE || mode == EPI_GELU)) {
+      CUtensorMap to;
+      if (get_tmap(ep.out, M, N, ep.ldo, 32, true, &to, err, 32)) return -2;
+      return mode == EPI_STORE ? tc_launch_ws<EPI_STORE>(ta, tb, to, M, N, K, ep, s, grid, err)
+                               : tc_launch_ws<EPI_GELU>(ta, tb, to, M, N, K, ep, s, grid, err);
+    }
     if (tma_out) {
       CUtensorMap to;
       if (get_tmap(ep.out, M, N, ep.ldo, 32, true, &to, err)) return -2;

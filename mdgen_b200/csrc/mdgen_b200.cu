@@ -121,6 +121,7 @@ struct mdgen_handle {
   float *h = nullptr, *xn = nullptr, *qkv = nullptr, *att = nullptr, *hid = nullptr, *cond = nullptr;
   float* ybuf = nullptr;   // gate * branch output of the out-proj / fc2 GEMMs when the residual add is fused into ln_mod
   int fuse_resid_ln = 0;   // 1: residual add in ln_mod_kernel (EPI_GATE GEMM epilogues; measured neutral: the bytes only move); 0 (default): in the GEMM epilogue
+  int gemm_dbg = 0;          // measurement switches forwarded to the tensor-core GEMM (Epilogue::dbg)
   float *xi = nullptr, *xni = nullptr, *proj = nullptr, *cat = nullptr, *qkvi = nullptr, *atti = nullptr,
         *hidi = nullptr, *frot = nullptr, *ftrans = nullptr, *fmask = nullptr, *ipa_out = nullptr;
   float *tvals = nullptr, *sinus = nullptr, *h1 = nullptr, *st = nullptr, *mod = nullptr, *dt = nullptr;
@@ -370,6 +371,7 @@ int gemm(mdgen_handle* h, cudaStream_t s, int mode, const float* A, int lda, con
   const bool in_bf16 = half_fmt != 0;
   Epilogue ep = ep_in;
   ep.half_fmt = half_fmt;
+  ep.dbg = h->gemm_dbg;
 #ifndef MDGEN_NO_TC
   if (h->use_tc && W_tc && M >= h->tc_min_rows && tc_gemm_supported(N, K, in_bf16)) {
     int rc = tc_gemm_launch(mode, A, lda, W_tc, ldw, M, N, K, ep, s, &h->err, in_bf16, out_bf16);
@@ -1189,6 +1191,7 @@ int mdgen_set_option(mdgen_handle* h, const char* key, int64_t value) {
   else if (k == "gemm_bf16") h->gemm_bf16 = (int)value;
   else if (k == "use_graph") h->use_graph = (int)value;
   else if (k == "fuse_resid_ln") h->fuse_resid_ln = (int)value;
+  else if (k == "gemm_dbg") h->gemm_dbg = (int)value;
   else if (k == "reuse_cond") { h->reuse_cond = (int)value; if (!value) h->cond_tokens = 0; }
   else if (k == "graph_max_tokens") h->graph_max_tokens = value;
   else if (k == "profile") {
