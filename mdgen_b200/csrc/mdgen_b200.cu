@@ -20,6 +20,7 @@
 #include "gemm_tc.cuh"
 #include "attention_tc.cuh"
 #include "attention_v8.cuh"
+#include "embed_step.cuh"
 #endif
 
 using namespace mdgen;
@@ -574,9 +575,16 @@ int run_step(mdgen_handle* h, cudaStream_t s, const mdgen_cond* c, const float* 
   // ---------------- token embedding  (latent_model.py:233-246)
   {
     ProfScope ps(h, s, "embed");
+#ifndef MDGEN_NO_TC
+    if (embed_step_configure() != cudaSuccess) { h->err = "cudaFuncSetAttribute(embed_step_kernel) failed"; return MDGEN_E_CUDA; }
+    embed_step_kernel<<<(unsigned)((N + kEsTok - 1) / kEsTok), kC, kEsSmemBytes, s>>>(
+        x_in, D, h->w_lat, h->cond, h->ipa_out, h->trunk_precomputed ? step_ptr : nullptr, (long long)B * L * kC,
+        h->h, N, T, L);
+#else
     embed_kernel<1><<<(unsigned)((N + kEmbedTok - 1) / kEmbedTok), kC, 0, s>>>(
         x_in, D, h->w_lat, nullptr, nullptr, nullptr, nullptr, nullptr, h->cond, h->ipa_out,
         h->trunk_precomputed ? step_ptr : nullptr, (long long)B * L * kC, h->h, N, T, L);
+#endif
     CHECK_LAUNCH(h);
   }
 
