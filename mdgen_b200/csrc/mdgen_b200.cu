@@ -650,7 +650,7 @@ int run_step(mdgen_handle* h, cudaStream_t s, const mdgen_cond* c, const float* 
   {
     ProfScope ps(h, s, "final");
     int off = n * 15 * kC;
-    int blocks = (int)std::min<long long>((N + 7) / 8, 148 * 8);
+    int blocks = (int)std::min<long long>((N + 15) / 16, 148 * 2);   // 2 resident blocks per SM (124 registers): W staged once each
     size_t smem = (size_t)D * kC * sizeof(float);
     if (euler)
       final_kernel<true><<<blocks, 256, smem, s>>>(h->h, modm, off, off + kC, h->w_fin, h->b_fin, D, x_in,
