@@ -192,6 +192,10 @@ int64_t mdgen_launch_count(const mdgen_handle* h);
  *   "reuse_cond"    1: mdgen_forward keeps the conditioning embedding of its previous call (same cond object and
  *                   shapes: the stages of one adaptive ODE solve); the caller resets it to 0 afterwards
  *   "emu_bf16"      precision experiments (tools/diag_precision.py);  "profile" 1 = per-family CUDA-event timing
+ *   "gemm_dbg"      measurement switches of the tcgen05 GEMMs, OUTPUT UNDEFINED: bit 0 no operand loads, bit 1 no MMAs
+ *                   (profiles/r2_gemm_epilogue.md: which of fill / MMA / epilogue bounds a GEMM)
+ * Environment (read once per process): MDGEN_NO_TMA_OUT=1 keeps the 16-bit-output GEMMs on the shared-memory-transpose
+ * epilogue, MDGEN_NO_WS=1 keeps the K <= 384 GEMMs on the tile-streaming kernel (A/B switches for the same file).
  * Unknown keys return MDGEN_E_INVALID. */
 int mdgen_set_option(mdgen_handle* h, const char* key, int64_t value);
 int64_t mdgen_get_option(const mdgen_handle* h, const char* key);

@@ -1223,6 +1223,7 @@ int64_t mdgen_get_option(const mdgen_handle* h, const char* key) {
   if (k == "gemm_bf16") return h->gemm_bf16;
   if (k == "use_graph") return h->use_graph;
   if (k == "fuse_resid_ln") return h->fuse_resid_ln;
+  if (k == "gemm_dbg") return h->gemm_dbg;
   if (k == "graph_replays") return h->graph_replays;
   if (k == "profile") return h->profile;
   if (k == "modw") return h->modw;

@@ -97,3 +97,31 @@ def test_synthetic_batch_is_rigid():
     eye = torch.eye(3).expand_as(R)
     assert torch.allclose(R @ R.transpose(-1, -2), eye, atol=1e-5)
     assert torch.allclose(torch.linalg.det(R), torch.ones(2, 5, 4), atol=1e-5)
+
+
+def test_fc1_gelu_polynomial_constants():
+    """The one-MUFU erf-GELU of the fc1 epilogue (csrc/gemm_tc.cuh gelu_fast2): gelu = max(x,0) - |x|/2 erfc(|x|/sqrt 2)
+    with erfc(z) = 2^(z P(z)), z clamped to 4. Evaluate the hex constants of the source in float32, in the kernel's
+    operation order, against torch's exact erf-GELU (layers.py:84 nn.GELU())."""
+    import struct
+    import numpy as np
+    src = open(os.path.join(os.path.dirname(__file__), "..", "mdgen_b200", "csrc", "gemm_tc.cuh")).read()
+    body = src[src.index("void gelu_fast2(float& x0, float& x1)"):]
+    body = body[:body.index("\n}\n")]
+    consts = {k: np.float32(struct.unpack("<f", struct.pack("<I", int(v, 16)))[0])
+              for k, v in re.findall(r"(kC\d|kNegRsqrt2) = splat2\(0x([0-9A-Fa-f]{8})u\)", body)}
+    assert set(consts) == {f"kC{i}" for i in range(7)} | {"kNegRsqrt2"}
+    g = torch.Generator().manual_seed(0)
+    x = torch.cat([torch.linspace(-12, 12, 400001), torch.randn(200000, generator=g) * 2]).numpy().astype(np.float32)
+    z = np.minimum(np.abs(x) * np.float32(0.70710678118654752440), np.float32(4.0))
+    p = np.full_like(z, consts["kC6"])
+    for i in range(5, -1, -1):
+        p = (p.astype(np.float64) * z + consts[f"kC{i}"]).astype(np.float32)      # fma.rn.f32x2: one rounding
+    q = (p * z).astype(np.float32)
+    e = np.exp2(q.astype(np.float64)).astype(np.float32)
+    out = ((z * consts["kNegRsqrt2"]).astype(np.float32).astype(np.float64) * e + np.maximum(x, 0)).astype(np.float32)
+    ref = torch.nn.functional.gelu(torch.from_numpy(x).double()).numpy()
+    err = np.abs(out - ref)
+    assert err.max() < 6e-7, err.max()
+    # ex2.approx is good to 2 ulp: its contribution is bounded by |x|/2 * erfc * 2^-22 < 1e-7
+    assert (err / (np.abs(ref) + 1e-3)).max() < 2e-4
