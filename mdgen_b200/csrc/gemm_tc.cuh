@@ -105,6 +105,15 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory descriptor, K-major operand, SWIZZLE_128B (cute::UMMA::SmemDescriptor):
@@ -538,18 +547,18 @@ __global__ void __launch_bounds__(128 + 32 * tc_epi_warps(MODE), 1) gemm_tc_kern
 // only, 0.197 ms with operand fills only and 0.255 ms with both -- each 128 x 192 tile pulls 98 KB of A AND 147 KB of W
 // from L2 for 18.9 MFLOP. Here a CTA owns ONE 192-row block of W for its whole life (147 KB resident in shared memory,
 // loaded once) and walks down the token rows of that column block, so a tile costs 98 KB of operand fill instead of 245.
-//   warp 0: TMA producer (W block once, then a 3-stage ring of 128 x 64 A blocks)   warp 1: MMA issuer
-//   warp 2: TMEM allocator        warps 4-15: epilogue, bulk-tensor stores of 32 x 32 chunks (2 KB staging per warp)
+//   warp 0: TMA producer (W block once, then a 4-stage ring of 128 x 64 A blocks)   warp 1: MMA issuer
+//   warp 2: TMEM allocator        warps 4-15: epilogue, bulk-tensor stores of 32 x 16 chunks (1 KB staging per warp)
 // Measured (profiles/r2_gemm_epilogue.md): the ring's depth IN TIME is what bounds these K = 384 GEMMs, not bytes: QKV takes
-// 0.51 / 0.33 / 0.24 ms with a 1 / 2 / 3-deep A ring (round trip MMA retire -> refill -> data landed ~0.7 us against 0.23 us
+// 0.51 / 0.33 / 0.24 / 0.23 ms with a 1 / 2 / 3 / 4-deep A ring (round trip MMA retire -> refill -> data landed ~0.7 us against 0.23 us
 // of MMA work per K-block), an L2 prefetch of A ahead of the loads and a single load+MMA thread were both slower.
 // CTA c works on column block c % n_blocks; the CTAs of one column block interleave its row tiles, so the CTAs that read
 // the same A tile do so at about the same time (one DRAM read, the other column blocks hit L2).
 constexpr int WS_MAXKB = 6;                                  // K <= 6 x 64
-constexpr int WS_ASTAGES = 3;
+constexpr int WS_ASTAGES = 4;
 constexpr int WS_A_BYTES = TC_BM * 128;                      // 16 KB: 128 rows x 64 16-bit elements
 constexpr int WS_B_BYTES = TC_BN * 128;                      // 24 KB per K-block of the resident W block
-constexpr int WS_STG_BYTES = 12 * 2048;                      // 32 rows x 64 B per epilogue warp
+constexpr int WS_STG_BYTES = 12 * 1024;                      // 32 rows x 32 B per epilogue warp
 constexpr int WS_SMEM_BYTES = WS_MAXKB * WS_B_BYTES + WS_ASTAGES * WS_A_BYTES + 1024 /*barriers*/ + WS_STG_BYTES + 1024 /*align*/;
 
 template <int MODE>
@@ -657,12 +666,13 @@ __global__ void __launch_bounds__(512, 1) gemm_tc_ws_kernel(const __grid_constan
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue warps (TMEM -> regs -> swizzled 32 x 32 chunk -> bulk-tensor store) ==========
+    // ===================== epilogue warps (TMEM -> regs -> swizzled 32 x 16 chunk -> bulk-tensor store) ==========
+    // 16-column chunks: 1 KB of staging per warp, which is what lets the A ring be 4 deep next to the resident W block
     const int q = warp & 3;
     const int slice = (warp - 4) >> 2;
-    const uint32_t stg = stg_base + (warp - 4) * 2048;                     // 32 rows x 64 B, swizzle-64B
-    const uint32_t row_addr = stg + lane * 64;
-    const uint32_t sw = (uint32_t)((lane >> 1) & 3);
+    const uint32_t stg = stg_base + (warp - 4) * 1024;                     // 32 rows x 32 B, swizzle-32B
+    const uint32_t row_addr = stg + lane * 32;
+    const uint32_t sw = (uint32_t)((lane >> 2) & 1);
     const bool f16 = ep.half_fmt == kFmtF16;
     uint32_t it = 0;
     for (long long mt = rank; mt < m_blocks; mt += group, ++it) {
@@ -672,22 +682,22 @@ __global__ void __launch_bounds__(512, 1) gemm_tc_ws_kernel(const __grid_constan
       mbar_wait(tfull_bar(buf), bphase);
       tc_fence_after();
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        float4 b4[8];
+      for (int c = 0; c < 4; ++c) {
+        float4 b4[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          b4[j] = ep.bias ? *reinterpret_cast<const float4*>(ep.bias + nc + c * 32 + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
-        uint32_t v[32];
-        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * TC_BN + slice * 64 + c * 32, v);
+        for (int j = 0; j < 4; ++j)
+          b4[j] = ep.bias ? *reinterpret_cast<const float4*>(ep.bias + nc + c * 16 + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        uint32_t v[16];
+        tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + buf * TC_BN + slice * 64 + c * 16, v);
         tc_ld_wait();
-        if (c == 1) {                                       // accumulator is in registers: hand the buffer back to the MMA warp
+        if (c == 3) {                                       // accumulator is in registers: hand the buffer back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty_bar(buf));
         }
         auto finish = [&](auto is_f16) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < 4; ++j) {
             float a0 = __uint_as_float(v[4 * j]) + b4[j].x, a1 = __uint_as_float(v[4 * j + 1]) + b4[j].y;
             float a2 = __uint_as_float(v[4 * j + 2]) + b4[j].z, a3 = __uint_as_float(v[4 * j + 3]) + b4[j].w;
             if (MODE == EPI_GELU) { gelu_fast2(a0, a1); gelu_fast2(a2, a3); }
@@ -699,14 +709,14 @@ __global__ void __launch_bounds__(512, 1) gemm_tc_ws_kernel(const __grid_constan
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous chunk's store has read the staging tile
         __syncwarp();
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < 2; ++u)
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_addr + ((((uint32_t)u) ^ sw) << 4)),
                        "r"(v[4 * u]), "r"(v[4 * u + 1]), "r"(v[4 * u + 2]), "r"(v[4 * u + 3]) : "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) {
           asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
-                       ::"l"(reinterpret_cast<uint64_t>(&tmO)), "r"(nc + c * 32), "r"(m0), "r"(stg) : "memory");
+                       ::"l"(reinterpret_cast<uint64_t>(&tmO)), "r"(nc + c * 16), "r"(m0), "r"(stg) : "memory");
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       }
@@ -769,7 +779,7 @@ inline PFN_encodeTiled get_encode_fn(std::string* err) {
 }
 
 // 2-D fp32 row-major [rows, cols] (leading dimension ld elements), box = [box_rows, 32 cols], SWIZZLE_128B
-// (box_cols = 32 with 16-bit elements: 64-byte rows, SWIZZLE_64B -- the store chunks of the weight-stationary kernel)
+// (box_cols = 16 with 16-bit elements: 32-byte rows, SWIZZLE_32B -- the store chunks of the weight-stationary kernel)
 inline int make_tmap_2d(CUtensorMap* map, const void* ptr, long long rows, int cols, int ld, int box_rows,
                         bool bf16, std::string* err, int box_cols = 0) {
   PFN_encodeTiled fn = get_encode_fn(err);
@@ -777,12 +787,13 @@ inline int make_tmap_2d(CUtensorMap* map, const void* ptr, long long rows, int c
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * (bf16 ? 2 : 4)};
   if (!box_cols) box_cols = bf16 ? 64 : TC_BK;                                   // 128-byte rows either way
-  const bool sw64 = box_cols * (bf16 ? 2 : 4) == 64;
+  const int box_bytes = box_cols * (bf16 ? 2 : 4);
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                   const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  box_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : (box_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B),
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -896,7 +907,7 @@ inline int tc_gemm_launch(int mode, const void* A, int lda, const void* W, int l
                          ep.round_out == 0 && M < (1ll << 31);
     if (tma_out && !tc_no_ws() && K <= WS_MAXKB * 64 && tiles >= 4ll * num_sms && N / TC_BN <= grid && (mode == EPI_STORE || mode == EPI_GELU)) {
       CUtensorMap to;
-      if (get_tmap(ep.out, M, N, ep.ldo, 32, true, &to, err, 32)) return -2;
+      if (get_tmap(ep.out, M, N, ep.ldo, 32, true, &to, err, 16)) return -2;
       return mode == EPI_STORE ? tc_launch_ws<EPI_STORE>(ta, tb, to, M, N, K, ep, s, grid, err)
                                : tc_launch_ws<EPI_GELU>(ta, tb, to, M, N, K, ep, s, grid, err);
     }
