@@ -139,7 +139,8 @@ __global__ void ln_affine_kernel(const float* __restrict__ x, float* __restrict_
 // staged in shared memory, so global reads/writes are coalesced along c.
 //   MODE 0 (once per sampling call): cond[n,c] = b_lat[c] + pos[l,c] + Wc[c,:]·x_cond[n,:] + b_c[c]
 //                                                + E_mask[x_cond_mask[n]][c]
-//   MODE 1 (every step)            : h[n,c] = Wl[c,:]·x[n,:] + cond[n,c] + ipa[b,l,c]
+//   MODE 1 (every step; builds without the tensor-core kernels only - the default path runs embed_step_kernel,
+//           csrc/embed_step.cuh): h[n,c] = Wl[c,:]·x[n,:] + cond[n,c] + ipa[b,l,c]
 constexpr int kEmbedTok = 128;  // tokens per block (amortises the per-thread weight-row load)
 template <int MODE>
 __global__ void __launch_bounds__(kC) embed_kernel(
@@ -164,49 +165,6 @@ __global__ void __launch_bounds__(kC) embed_kernel(
   float bsum = (MODE == 0) ? (bias0[c] + bias1[c]) : 0.f;
   if (MODE == 1 && step_ptr) ipa += (size_t)(*step_ptr) * ipa_step_stride;   // trunk output of this Euler step
   __syncthreads();
-#ifdef MDGEN_EMBED_INCREMENTAL   // experiment, not yet validated on hardware: ~1.8x fewer instructions per token
-  // sample index b / position inside the sample / residue index l of the block's first token; the values of
-  // the following tokens are stepped incrementally (per-token divisions and 64-bit index arithmetic used to
-  // cost ~3x the useful FMA work of this kernel)
-  const long long TL = (long long)T * L;
-  long long b = n0 / TL;
-  long long rem = n0 - b * TL;
-  int l = (int)(rem % L);
-  const float* cond_p = (MODE == 1) ? cond + (size_t)n0 * kC + c : nullptr;
-  const float* ipa_b = (MODE == 1) ? ipa + (size_t)b * L * kC + c : nullptr;    // trunk rows of sample b
-  float* out_p = out + (size_t)n0 * kC + c;
-  constexpr int U = 4;                 // tokens in flight per thread (independent global loads)
-  for (int i = 0; i < nt; i += U) {
-    float add[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      add[u] = 0.f;
-      if (i + u < nt) {
-        if (MODE == 0) {
-          add[u] = bsum + emask[(size_t)ms[i + u] * kC + c];
-          if (pos) add[u] += pos[(size_t)l * kC + c];
-        } else {
-          add[u] = cond_p[(size_t)(i + u) * kC] + ipa_b[(size_t)l * kC];
-        }
-        if (++l == L) l = 0;                                   // step to the next token
-        if (++rem == TL) { rem = 0; ++b; if (MODE == 1) ipa_b = ipa + (size_t)b * L * kC + c; }
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (i + u < nt) {
-        float s = 0.f;
-#pragma unroll
-        for (int k4 = 0; k4 < 7; ++k4) {     // 128-bit broadcast reads of the token's latent (w[k] = 0 for k >= D)
-          const float4 xv = *reinterpret_cast<const float4*>(&xs[i + u][4 * k4]);
-          s = fmaf(w[4 * k4], xv.x, s); s = fmaf(w[4 * k4 + 1], xv.y, s);
-          s = fmaf(w[4 * k4 + 2], xv.z, s); s = fmaf(w[4 * k4 + 3], xv.w, s);
-        }
-        out_p[(size_t)(i + u) * kC] = s + add[u];
-      }
-    }
-  }
-#else
   // sample index / residue index of the block's first token; per-token values follow incrementally
   // (a 64-bit division per token and thread used to dominate this kernel)
   const long long TL = (long long)T * L;
@@ -246,7 +204,6 @@ __global__ void __launch_bounds__(kC) embed_kernel(
       }
     }
   }
-#endif
 }
 
 // ---------------------------------------------------------------------------------------------
